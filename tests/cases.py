@@ -1,0 +1,66 @@
+"""Seeded test configurations shared by oracle/make_golden.py, the CPU tests and the GPU parity tests."""
+import importlib
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+pkg = importlib.import_module("dist-renderer_b200")
+synth = importlib.import_module("dist-renderer_b200.synth")
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+# name -> recipe.  cam: ('front', dist) or ('lookat', az, el, dist, focal_scale)
+CASES = {
+    "c1_recursive_64": dict(decoder="B", hw=(64, 64), cam=("front", 1.6), march_step=50, buffer_size=5,
+                            kind="recursive"),
+    "c1_decoderA_64": dict(decoder="A", hw=(64, 64), cam=("front", 1.6), march_step=50, buffer_size=5,
+                           kind="recursive"),
+    "trivial_40": dict(decoder="B", hw=(40, 40), cam=("front", 1.6), march_step=50, buffer_size=5, kind="trivial"),
+    "pyramid_64": dict(decoder="B", hw=(64, 64), cam=("front", 1.6), march_step=50, buffer_size=5,
+                       kind="pyramid_recursive"),
+    "c3_lookat_56": dict(decoder="B", hw=(56, 56), cam=("lookat", 40.0, 25.0, 2.5, 1.2 * 2.5 / 1.6),
+                         march_step=100, buffer_size=3, kind="recursive"),
+    "ragged_37x53": dict(decoder="B", hw=(37, 53), cam=("lookat", 200.0, -30.0, 1.9, 1.0), march_step=30,
+                         buffer_size=5, kind="recursive"),
+    "inside_32": dict(decoder="B", hw=(32, 32), cam=("front", 0.8), march_step=40, buffer_size=5, kind="recursive"),
+}
+
+_DEC = {}
+
+
+def decoder(kind):
+    if kind not in _DEC:
+        _DEC[kind] = synth.make_decoder(kind)
+    return _DEC[kind]
+
+
+def camera(spec, hw):
+    H, W = hw
+    if spec[0] == "front":
+        R, T = synth.front_camera(spec[1])
+        K = synth.intrinsic(H, W)
+    else:
+        _, az, el, dist, fs = spec
+        R, T = synth.lookat_camera(az, el, dist)
+        K = synth.intrinsic(H, W, focal_scale=fs)
+    return K, R, T
+
+
+LOSS_W = torch.tensor([0.3, -0.2, 0.5])
+
+
+def scalar_loss(out):
+    """A fixed scalar of render()'s outputs used to compare gradients: depth on the mask, min_sdf, normal."""
+    depth, normal, mask, min_sdf = out
+    m = mask.bool()
+    return depth[m].sum() + 3.0 * min_sdf.sum() + (normal * LOSS_W.to(normal)).sum()
+
+
+def weights_checksum(dec):
+    with torch.no_grad():
+        return float(sum(p.double().abs().sum() for p in dec.state_dict().values()))

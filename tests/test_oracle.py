@@ -1,0 +1,98 @@
+"""CPU: pin oracle/sdf_oracle.py against (a) golden fixtures written from the real reference and
+(b) the real reference itself where /root/reference is present (the build container)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import cases
+from oracle import ref_shim
+from oracle.sdf_oracle import OracleSDFRenderer, decode_sdf, decode_sdf_gradient
+
+
+def _rel(a, b):
+    a, b = torch.as_tensor(a, dtype=torch.float64), torch.as_tensor(b, dtype=torch.float64)
+    return float((a - b).norm() / (b.norm() + 1e-300))
+
+
+def _run_oracle(cs, dtype=torch.float32):
+    dec = cases.decoder(cs["decoder"])
+    if dtype == torch.float64:
+        import copy
+        dec = copy.deepcopy(dec).double()
+    K, R, T = cases.camera(cs["cam"], cs["hw"])
+    ren = OracleSDFRenderer(dec, K, img_hw=cs["hw"], march_step=cs["march_step"], buffer_size=cs["buffer_size"],
+                            dtype=dtype)
+    lat = cases.synth.make_latent().to(dtype).requires_grad_(True)
+    Rg, Tg = R.to(dtype).requires_grad_(True), T.to(dtype).requires_grad_(True)
+    out = ren.render(lat, Rg, Tg, ray_marching_type=cs["kind"])
+    cases.scalar_loss(out).backward()
+    return out, (lat.grad, Rg.grad, Tg.grad)
+
+
+@pytest.mark.parametrize("name", sorted(cases.CASES))
+def test_oracle_matches_golden(name):
+    """Golden = outputs of the unmodified reference.  Same torch build, same ops -> expect (near) bit equality."""
+    cs = cases.CASES[name]
+    gold = np.load(os.path.join(cases.GOLDEN_DIR, name + ".npz"))
+    assert abs(cases.weights_checksum(cases.decoder(cs["decoder"])) - float(gold["weights_checksum"])) < 1e-6
+    out, grads = _run_oracle(cs)
+    assert int((out[2].numpy() != gold["mask"]).sum()) == 0
+    m = gold["mask"].astype(bool)
+    if m.any():
+        assert _rel(out[0].detach().numpy()[m], gold["depth"][m]) < 1e-6
+        assert _rel(out[1].detach().numpy(), gold["normal"]) < 1e-5
+    assert _rel(out[3].detach().numpy(), gold["min_sdf"]) < 1e-6
+    for g, key in zip(grads, ("g_latent", "g_R", "g_T")):
+        assert _rel(g.numpy(), gold[key]) < 1e-4, key
+
+
+def test_oracle_decoder_points_golden():
+    gold = np.load(os.path.join(cases.GOLDEN_DIR, "decoder_points.npz"))
+    dec, lat = cases.decoder("B"), cases.synth.make_latent()
+    pts = torch.from_numpy(gold["points"])
+    assert _rel(decode_sdf(dec, lat, pts, clamp_dist=None).detach().numpy(), gold["sdf"]) < 1e-6
+    p = pts.clone().requires_grad_(True)
+    assert _rel(decode_sdf_gradient(dec, lat, p).detach().numpy(), gold["grad"]) < 1e-5
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="reference tree not present (GPU box)")
+@pytest.mark.parametrize("name", ["trivial_40", "inside_32"])
+def test_oracle_matches_live_reference(name):
+    cs = cases.CASES[name]
+    Rmod, _, RefDecoder = ref_shim.load()
+    dec = cases.decoder(cs["decoder"])
+    ref = RefDecoder(dec.latent_size, **cases.synth.STANDARD_SPEC).eval()
+    ref.load_state_dict(dec.state_dict())
+    K, R, T = cases.camera(cs["cam"], cs["hw"])
+    ren = Rmod.SDFRenderer(ref, K, img_hw=cs["hw"], march_step=cs["march_step"], buffer_size=cs["buffer_size"],
+                           use_gpu=False)
+    a = ren.render(cases.synth.make_latent(), R, T, ray_marching_type=cs["kind"], no_grad=True)
+    b, _ = _run_oracle(cs)
+    assert int((a[2] != b[2]).sum()) == 0
+    for i in (0, 1, 3):
+        assert _rel(b[i].detach(), a[i]) < 1e-6
+
+
+def test_fp64_twin_noise_floor():
+    """The fp64 twin bounds how far a faithful fp32 implementation may sit from the fp32 reference."""
+    cs = cases.CASES["trivial_40"]
+    o32, _ = _run_oracle(cs)
+    o64, _ = _run_oracle(cs, torch.float64)
+    m = o32[2].bool() & o64[2].bool()
+    assert int((o32[2] != o64[2]).sum()) <= 4
+    assert _rel(o32[0].detach()[m], o64[0].detach()[m]) < 1e-4
+
+
+def test_no_valid_depth_raises():
+    """No ray meets the unit sphere: the reference dies in `init_zdepth_valid.max()` on an empty tensor
+    (renderer.py:271, RuntimeError) before reaching ValueError('No valid depth.') (renderer.py:214-215)."""
+    dec = cases.decoder("B")
+    K = cases.synth.intrinsic(8, 8)
+    ren = OracleSDFRenderer(dec, K, img_hw=(8, 8))
+    R, T = cases.synth.front_camera(50.0)      # unit sphere covers < 1 pixel and no pixel centre hits it
+    K[0, 2] += 400.0                            # shift principal point so every ray misses
+    ren = OracleSDFRenderer(dec, K, img_hw=(8, 8))
+    with pytest.raises((ValueError, RuntimeError)):
+        ren.render_depth(cases.synth.make_latent(), R, T, no_grad=True)
