@@ -1,2 +1,10 @@
-"""B200-native differentiable sphere tracing -- drop-in for DIST-Renderer's SDFRenderer hot path."""
+"""B200-native differentiable sphere tracing -- drop-in for DIST-Renderer's SDFRenderer hot path.
+
+Public surface (mirrors the reference's names):
+  SDFRenderer                      core/sdfrenderer/renderer.py:12
+  decode_sdf, decode_sdf_gradient  core/utils/decoder_utils.py:53,76
+  Decoder, load_decoder            core/graph/deep_sdf_decoder.py:18, core/utils/decoder_utils.py:7
+"""
 from .decoder import Decoder, load_decoder  # noqa: F401
+from .functional import decode_sdf, decode_sdf_gradient  # noqa: F401
+from .renderer import SDFRenderer  # noqa: F401

@@ -1,0 +1,65 @@
+// Shared device/host helpers for libdist_b200.so
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/dist_b200.h"
+
+namespace dist {
+
+void set_error(const char* fmt, ...);
+int num_sms();
+
+#define DIST_CHECK_CUDA(expr)                                                                   \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess) {                                                                    \
+      ::dist::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return DIST_E_CUDA;                                                                       \
+    }                                                                                           \
+  } while (0)
+
+#define DIST_REQUIRE(cond, ...)                 \
+  do {                                          \
+    if (!(cond)) {                              \
+      ::dist::set_error(__VA_ARGS__);           \
+      return DIST_E_INVALID;                    \
+    }                                           \
+  } while (0)
+
+__host__ __device__ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// Device copy of the network description (passed by value as a kernel parameter).
+struct NetDev {
+  int n_layers, latent_in, use_tanh;
+  int K[DIST_MAX_LAYERS], N[DIST_MAX_LAYERS];
+  const float* Wt[DIST_MAX_LAYERS];
+  const float* W[DIST_MAX_LAYERS];
+  const float* bias[DIST_MAX_LAYERS];
+};
+
+int make_netdev(const dist_net_t* net, NetDev* out);
+
+// engines (mlp_simt.cu / mlp_tc.cu).  mode: 0 forward, 1 input-gradient, 2 backward replay
+struct MlpArgs {
+  const float* points;      // [n][3]
+  int64_t n_host;
+  const int32_t* n_dev;
+  float clamp_dist;         // <= 0: no clamp
+  float* sdf;               // [n] or null
+  float* grad;              // [n][3] or null (modes 1,2: coef * dsdf/dxyz)
+  const float* coef;        // [n] or null (=1)
+  const uint8_t* use_clamp; // [n] or null (= clamp_dist > 0 for every row)
+  float* acc0;              // [N0] or null
+  float* accl;              // [Nl] or null
+  int64_t* rows_evaluated;  // optional counter (+= n)
+};
+int mlp_simt_launch(const NetDev& net, int mode, const MlpArgs& a, cudaStream_t stream);
+int mlp_tc_launch(const dist_net_t* net, const NetDev& nd, int mode, const MlpArgs& a, cudaStream_t stream);
+
+inline int mlp_launch(const dist_net_t* net, const NetDev& nd, int engine, int mode, const MlpArgs& a,
+                      cudaStream_t stream) {
+  if (engine == DIST_ENGINE_TC) return mlp_tc_launch(net, nd, mode, a, stream);
+  return mlp_simt_launch(nd, mode, a, stream);
+}
+
+}  // namespace dist

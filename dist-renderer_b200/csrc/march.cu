@@ -1,0 +1,428 @@
+// Ray set-up, sphere tracing state machine, sample selection, normals and backward row generation.
+//
+// These are the per-ray (elementwise) parts of the path; every decoder evaluation goes through the engines in
+// mlp_simt.cu / mlp_tc.cu.  Arithmetic mirrors the reference's op order (separately rounded mul/add where PyTorch
+// issues separate elementwise ops): this file is compiled with -fmad=false and uses fmaf() only where the
+// reference's op is a matmul.
+//
+// Reference: core/sdfrenderer/renderer.py:171-282 (rays, unit-sphere clip), :472-583 (marching), :304-420 (sample
+// selection and depth estimate), :836-910 (render_depth / render_normal).
+#include <cuda_runtime.h>
+#include <math.h>
+#include "common.cuh"
+
+namespace dist {
+namespace {
+
+struct Cam {
+  float Kinv[9], M[9];
+  const float* R;
+  const float* c;
+  int W, H, row0, row_step, n_rows;
+  float radius;
+};
+
+__device__ __forceinline__ int warp_append(int32_t* counter, bool pred) {
+  const unsigned m = __ballot_sync(0xffffffffu, pred);
+  if (m == 0) return -1;
+  const int lane = threadIdx.x & 31;
+  const int leader = __ffs(m) - 1;
+  int base = 0;
+  if (lane == leader) base = atomicAdd(counter, __popc(m));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  return pred ? base + __popc(m & ((1u << lane) - 1)) : -1;
+}
+
+// unit ray through local pixel lp, world frame (renderer.py:39,190-200)
+__device__ __forceinline__ void pixel_ray(const Cam& cam, const float* R, int lp, float (&ray)[3]) {
+  const float x = (float)(lp % cam.W);
+  const float y = (float)(cam.row0 + (lp / cam.W) * cam.row_step);
+  float hc[3], v[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) hc[i] = fmaf(cam.Kinv[i * 3 + 2], 1.f, fmaf(cam.Kinv[i * 3 + 1], y, cam.Kinv[i * 3] * x));
+#pragma unroll
+  for (int i = 0; i < 3; ++i) v[i] = fmaf(R[6 + i], hc[2], fmaf(R[3 + i], hc[1], R[i] * hc[0]));
+  const float nrm = sqrtf(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]) + 1e-12f;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) ray[i] = v[i] / nrm;
+}
+
+// p = M^T (c + ray * depth)   (renderer.py:202-223, :119)
+__device__ __forceinline__ void point_on_ray(const Cam& cam, const float (&c)[3], const float (&ray)[3], float depth,
+                                             float (&p)[3]) {
+  float q[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) q[i] = ray[i] * depth + c[i];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) p[i] = fmaf(cam.M[6 + i], q[2], fmaf(cam.M[3 + i], q[1], cam.M[i] * q[0]));
+}
+
+__device__ __forceinline__ float clampf(float v, float c) { return fminf(fmaxf(v, -c), c); }
+
+// ---------------------------------------------------------------------------------------------- set-up
+__global__ void k_setup(Cam cam, dist_march_t mp, dist_workspace_t ws, float* Zdepth, uint8_t* mask, float* min_sdf,
+                        int P) {
+  const int lp = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool in = lp < P;
+  float R[9], c[3];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) R[i] = cam.R[i];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) c[i] = cam.c[i];
+  bool live = false;
+  float ray[3] = {0.f, 0.f, 1.f}, entry = 0.f;
+  if (in) {
+    pixel_ray(cam, R, lp, ray);
+    // renderer.py:225-239
+    const float ptq = (c[0] * ray[0] + c[1] * ray[1]) + c[2] * ray[2];
+    const float d0 = c[0] - ptq * ray[0], d1 = c[1] - ptq * ray[1], d2 = c[2] - ptq * ray[2];
+    const float dist = sqrtf(d0 * d0 + d1 * d1 + d2 * d2);
+    const bool hit = dist <= cam.radius;
+    // renderer.py:241-273
+    const float value = cam.radius * cam.radius - dist * dist;
+    const float chord = (value >= 0.f) ? 2.f * sqrtf(value) : 0.f;
+    const float cd = sqrtf((c[0] * c[0] + c[1] * c[1]) + c[2] * c[2]);
+    entry = (cd < cam.radius) ? 0.f : sqrtf(cd * cd - dist * dist) - chord / 2.0f;
+    const float ex = entry + chord;
+    ws.ray[lp] = ray[0]; ws.ray[P + lp] = ray[1]; ws.ray[2 * P + lp] = ray[2];
+    ws.entry[lp] = entry; ws.exit_[lp] = ex; ws.dist[lp] = dist; ws.z[lp] = 0.f;
+    ws.flags[lp] = hit ? 1 : 0;
+    ws.nreal[lp] = 0;
+    for (int b = 0; b < mp.buffer_size; ++b) {
+      ws.top_sdf[(size_t)b * P + lp] = 1.0f;  // filler entries: sdf 1, point 0 (renderer.py:539-540,555)
+      ws.top_zafter[(size_t)b * P + lp] = 0.f;
+      ws.top_zgen[(size_t)b * P + lp] = nanf("");
+#pragma unroll
+      for (int k = 0; k < 3; ++k) ws.top_pt[((size_t)b * 3 + k) * P + lp] = 0.f;
+    }
+    if (!hit) {
+      Zdepth[lp] = 1e11f; mask[lp] = 0;
+      min_sdf[lp] = dist + mp.threshold - cam.radius;  // renderer.py:863
+    }
+    live = hit && (mp.marching_type == DIST_MARCH_TRIVIAL || (0.f + entry < ex));  // renderer.py:526
+  }
+  const int idx = warp_append(ws.counts + 0, live);
+  if (idx >= 0) {
+    float p[3];
+    point_on_ray(cam, c, ray, entry + 0.f, p);
+    ws.list_a[idx] = lp;
+    ws.pts[(size_t)idx * 3] = p[0]; ws.pts[(size_t)idx * 3 + 1] = p[1]; ws.pts[(size_t)idx * 3 + 2] = p[2];
+  }
+}
+
+// appends the origin as one extra query row of step 0; counts[S+1] = counts[0] + 1 is the row count of that launch
+__global__ void k_append_origin(dist_workspace_t ws, int slot_total) {
+  const int n = ws.counts[0];
+  ws.pts[(size_t)n * 3] = 0.f; ws.pts[(size_t)n * 3 + 1] = 0.f; ws.pts[(size_t)n * 3 + 2] = 0.f;
+  ws.counts[slot_total] = n + 1;
+}
+
+// ---------------------------------------------------------------------------------------------- one march step
+__global__ void k_march_update(Cam cam, dist_march_t mp, dist_workspace_t ws, int step, int P) {
+  const int n = ws.counts[step];
+  const int32_t* cur = (step & 1) ? ws.list_b : ws.list_a;
+  int32_t* nxt = (step & 1) ? ws.list_a : ws.list_b;
+  const float* pts_cur = ws.pts + (size_t)(step & 1) * (size_t)(P + 1) * 3;       // points of this step
+  float* pts_nxt = ws.pts + (size_t)((step + 1) & 1) * (size_t)(P + 1) * 3;       // points of the next step
+  if (step == 0 && blockIdx.x == 0 && threadIdx.x == 0) ws.sdf_origin[0] = ws.sdf[n];
+  float c[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) c[i] = cam.c[i];
+  const int B = mp.buffer_size;
+  for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+    const int i = base + threadIdx.x;
+    bool live = false;
+    int lp = 0;
+    float znew = 0.f, entry = 0.f;
+    if (i < n) {
+      lp = cur[i];
+      const float sdf = ws.sdf[i];
+      const float px = pts_cur[(size_t)i * 3], py = pts_cur[(size_t)i * 3 + 1], pz = pts_cur[(size_t)i * 3 + 2];
+      const float zc = ws.z[lp];
+      entry = ws.entry[lp];
+      znew = zc + clampf(sdf, mp.clamp_dist) * mp.ratio;  // renderer.py:548-551
+      ws.z[lp] = znew;
+      ws.nreal[lp] = step + 1;
+      if (step == 0 && sdf > mp.threshold) ws.flags[lp] |= 2;  // renderer.py:581
+      // insert into the sorted top-B (smallest |sdf| first); replaces topk over the step lists (renderer.py:316-319)
+      const float asdf = fabsf(sdf);
+      int pos = B;
+      for (int b = 0; b < B; ++b)
+        if (asdf < fabsf(ws.top_sdf[(size_t)b * P + lp])) { pos = b; break; }
+      if (pos < B) {
+        for (int b = B - 1; b > pos; --b) {
+          ws.top_sdf[(size_t)b * P + lp] = ws.top_sdf[(size_t)(b - 1) * P + lp];
+          ws.top_zafter[(size_t)b * P + lp] = ws.top_zafter[(size_t)(b - 1) * P + lp];
+          ws.top_zgen[(size_t)b * P + lp] = ws.top_zgen[(size_t)(b - 1) * P + lp];
+#pragma unroll
+          for (int k = 0; k < 3; ++k)
+            ws.top_pt[((size_t)b * 3 + k) * P + lp] = ws.top_pt[((size_t)(b - 1) * 3 + k) * P + lp];
+        }
+        ws.top_sdf[(size_t)pos * P + lp] = sdf;
+        ws.top_zafter[(size_t)pos * P + lp] = znew;
+        ws.top_zgen[(size_t)pos * P + lp] = entry + zc;
+        ws.top_pt[((size_t)pos * 3 + 0) * P + lp] = px;
+        ws.top_pt[((size_t)pos * 3 + 1) * P + lp] = py;
+        ws.top_pt[((size_t)pos * 3 + 2) * P + lp] = pz;
+      }
+      if (step + 1 < mp.march_step) {
+        if (mp.marching_type == DIST_MARCH_TRIVIAL) live = true;
+        else live = (znew + entry < ws.exit_[lp]) && (asdf >= mp.threshold);  // renderer.py:559-561
+      }
+    }
+    const int idx = warp_append(ws.counts + step + 1, live);
+    if (idx >= 0) {
+      float ray[3] = {ws.ray[lp], ws.ray[P + lp], ws.ray[2 * P + lp]}, p[3];
+      point_on_ray(cam, c, ray, entry + znew, p);
+      nxt[idx] = lp;
+      pts_nxt[(size_t)idx * 3] = p[0]; pts_nxt[(size_t)idx * 3 + 1] = p[1]; pts_nxt[(size_t)idx * 3 + 2] = p[2];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- finalize
+__global__ void k_finalize(dist_march_t mp, dist_workspace_t ws, float* Zdepth, uint8_t* mask, float* min_sdf, int P) {
+  __shared__ int s_steps;
+  if (threadIdx.x == 0) {
+    int s = 0;
+    while (s < mp.march_step && ws.counts[s] > 0) ++s;  // executed steps (early break, renderer.py:562)
+    s_steps = s;
+  }
+  __syncthreads();
+  const int lp = blockIdx.x * blockDim.x + threadIdx.x;
+  if (lp >= P || !(ws.flags[lp] & 1)) return;
+  const int B = mp.buffer_size;
+  const int S = s_steps;
+  int nreal = ws.nreal[lp];
+  const float so = ws.sdf_origin[0];
+  const float zfin = ws.z[lp];
+  // renderer.py:562-567: a global early break before buffer_size steps pads the lists with copies of the last step
+  if (S < B && nreal == S && nreal > 0) {
+    int j = 0;
+    for (int b = 0; b < nreal; ++b)
+      if (ws.top_zafter[(size_t)b * P + lp] == zfin) j = b;
+    const int pad = B - nreal;
+    for (int b = nreal - 1; b > j; --b) {  // move the tail behind the copies
+      const int d = b + pad;
+      ws.top_sdf[(size_t)d * P + lp] = ws.top_sdf[(size_t)b * P + lp];
+      ws.top_zafter[(size_t)d * P + lp] = ws.top_zafter[(size_t)b * P + lp];
+      ws.top_zgen[(size_t)d * P + lp] = ws.top_zgen[(size_t)b * P + lp];
+      for (int k = 0; k < 3; ++k) ws.top_pt[((size_t)d * 3 + k) * P + lp] = ws.top_pt[((size_t)b * 3 + k) * P + lp];
+    }
+    for (int d = j + 1; d <= j + pad; ++d) {
+      ws.top_sdf[(size_t)d * P + lp] = ws.top_sdf[(size_t)j * P + lp];
+      ws.top_zafter[(size_t)d * P + lp] = ws.top_zafter[(size_t)j * P + lp];
+      ws.top_zgen[(size_t)d * P + lp] = ws.top_zgen[(size_t)j * P + lp];
+      for (int k = 0; k < 3; ++k) ws.top_pt[((size_t)d * 3 + k) * P + lp] = ws.top_pt[((size_t)j * 3 + k) * P + lp];
+    }
+    nreal = B;
+    ws.nreal[lp] = B;
+  }
+  const float s0 = ws.top_sdf[lp];
+  const float entry = ws.entry[lp];
+  const bool first_ok = (nreal == 0) || (ws.flags[lp] & 2);
+  const bool valid = (zfin + entry < ws.exit_[lp]) && (fabsf(s0) <= mp.threshold) &&
+                     (!mp.first_query_check || first_ok);  // renderer.py:574-582
+  min_sdf[lp] = (nreal > 0) ? s0 : so;  // renderer.py:382-390 (value of the re-query at the min-|sdf| point)
+  // renderer.py:407-408
+  float zz = ws.top_zafter[lp] + (1.f - mp.ratio) * clampf(s0, mp.clamp_dist);
+  if (mp.replay_grad_rounding) {  // renderer.py:414-417: z - s.detach()*ratio + s*ratio, value-neutral up to rounding
+    for (int b = 0; b < B; ++b) {
+      const float s = clampf((b < nreal) ? ws.top_sdf[(size_t)b * P + lp] : so, mp.clamp_dist);
+      const float a = s * mp.ratio;
+      zz = zz - a;
+      zz = zz + a;
+    }
+  }
+  Zdepth[lp] = entry + zz;  // renderer.py:868
+  mask[lp] = valid ? 1 : 0;
+}
+
+// ---------------------------------------------------------------------------------------------- normals
+__global__ void k_normal_gen(Cam cam, const float* Zdepth, const uint8_t* mask, int32_t* idx_out, float* pts,
+                             int32_t* count, int P) {
+  const int lp = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool on = lp < P && mask[lp] != 0;
+  const int idx = warp_append(count, on);
+  if (idx >= 0) {
+    float R[9], c[3], ray[3], p[3];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) R[i] = cam.R[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) c[i] = cam.c[i];
+    pixel_ray(cam, R, lp, ray);
+    point_on_ray(cam, c, ray, Zdepth[lp], p);
+    idx_out[idx] = lp;
+    pts[(size_t)idx * 3] = p[0]; pts[(size_t)idx * 3 + 1] = p[1]; pts[(size_t)idx * 3 + 2] = p[2];
+  }
+}
+
+__global__ void k_normal_finish(Cam cam, const int32_t* idx_in, const float* grad, const int32_t* count, int normalize,
+                                float* Znormal, int P) {
+  const int n = *count;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int lp = idx_in[i];
+    float g[3] = {grad[(size_t)i * 3], grad[(size_t)i * 3 + 1], grad[(size_t)i * 3 + 2]};
+    if (normalize) {  // renderer.py:171-178
+      const float nrm = sqrtf(g[0] * g[0] + g[1] * g[1] + g[2] * g[2]) + 1e-12f;
+      g[0] = g[0] / nrm; g[1] = g[1] / nrm; g[2] = g[2] / nrm;
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k)  // renderer.py:97 transform_matrix @ n
+      Znormal[(size_t)k * P + lp] = fmaf(cam.M[k * 3 + 2], g[2], fmaf(cam.M[k * 3 + 1], g[1], cam.M[k * 3] * g[0]));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- backward rows
+__global__ void k_bwd_gen(dist_march_t mp, dist_workspace_t ws, const float* gZ, const float* gM, int32_t* row_pix,
+                          float* pts, float* coef, int32_t* count, int P) {
+  const int lp = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool hit = lp < P && (ws.flags[lp] & 1);
+  const int B = mp.buffer_size;
+  const int nreal = hit ? ws.nreal[lp] : 0;
+  const float so = ws.sdf_origin[0];
+  const float gz = (hit && gZ) ? gZ[lp] : 0.f;
+  const float gm = (hit && gM) ? gM[lp] : 0.f;
+  for (int b = 0; b < B; ++b) {
+    float cf = 0.f;
+    if (hit) {
+      const float s = (b < nreal) ? ws.top_sdf[(size_t)b * P + lp] : so;
+      const bool cm = (s >= -mp.clamp_dist) && (s <= mp.clamp_dist);
+      cf = cm ? mp.ratio * gz : 0.f;  // renderer.py:414-417
+      if (b == 0) cf += gm;           // renderer.py:386 (unclamped re-query at the min-|sdf| sample)
+    }
+    const int idx = warp_append(count, cf != 0.f);
+    if (idx >= 0) {
+      row_pix[idx] = lp * DIST_MAX_BUFFER + b;
+      coef[idx] = cf;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) pts[(size_t)idx * 3 + k] = ws.top_pt[((size_t)b * 3 + k) * P + lp];
+    }
+  }
+}
+
+__global__ void k_bwd_scatter(Cam cam, dist_workspace_t ws, const int32_t* row_pix, const float* dpts,
+                              const int32_t* count, float* d_cam, float* d_ray, int P) {
+  const int n = *count;
+  float acc[3] = {0.f, 0.f, 0.f};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int lp = row_pix[i] / DIST_MAX_BUFFER, b = row_pix[i] % DIST_MAX_BUFFER;
+    const float zg = ws.top_zgen[(size_t)b * P + lp];
+    if (zg != zg) continue;  // filler / off-ray sample: no camera dependence
+    const float d[3] = {dpts[(size_t)i * 3], dpts[(size_t)i * 3 + 1], dpts[(size_t)i * 3 + 2]};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {  // p = M^T q  ->  dL/dq = M dL/dp
+      const float v = fmaf(cam.M[k * 3 + 2], d[2], fmaf(cam.M[k * 3 + 1], d[1], cam.M[k * 3] * d[0]));
+      acc[k] += v;
+      atomicAdd(d_ray + (size_t)k * P + lp, v * zg);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    float v = acc[k];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v != 0.f) atomicAdd(d_cam + k, v);
+  }
+}
+
+int make_cam(const dist_camera_t* cam, Cam* out) {
+  DIST_REQUIRE(cam && cam->R && cam->cam_pos, "camera: null pointer");
+  DIST_REQUIRE(cam->width > 0 && cam->n_rows > 0 && cam->row_step > 0, "camera: bad image/tile description");
+  DIST_REQUIRE((int64_t)cam->width * cam->n_rows < (int64_t)(1u << 31) / DIST_MAX_BUFFER, "camera: tile too large");
+  for (int i = 0; i < 9; ++i) { out->Kinv[i] = cam->Kinv[i]; out->M[i] = cam->M[i]; }
+  out->R = cam->R; out->c = cam->cam_pos;
+  out->W = cam->width; out->H = cam->height; out->row0 = cam->row0; out->row_step = cam->row_step;
+  out->n_rows = cam->n_rows; out->radius = cam->radius;
+  return DIST_OK;
+}
+
+}  // namespace
+
+// =============================================================================================== host entry points
+int render_depth_fwd(const dist_net_t* net, int engine, const dist_camera_t* camh, const dist_march_t* mp,
+                     const dist_workspace_t* ws, float* Zdepth, uint8_t* mask, float* min_sdf, int64_t* rows_eval,
+                     cudaStream_t st) {
+  Cam cam;
+  int rc = make_cam(camh, &cam);
+  if (rc) return rc;
+  NetDev nd;
+  rc = make_netdev(net, &nd);
+  if (rc) return rc;
+  DIST_REQUIRE(mp->buffer_size >= 1 && mp->buffer_size <= DIST_MAX_BUFFER, "buffer_size must be in [1,%d]", DIST_MAX_BUFFER);
+  DIST_REQUIRE(mp->march_step >= 1, "march_step must be >= 1");
+  DIST_REQUIRE(mp->marching_type == DIST_MARCH_TRIVIAL || mp->marching_type == DIST_MARCH_RECURSIVE, "bad marching_type");
+  const int P = cam.W * cam.n_rows;
+  const int S = mp->march_step;
+  DIST_CHECK_CUDA(cudaMemsetAsync(ws->counts, 0, sizeof(int32_t) * (S + 2), st));
+  const int tb = 256, gb = (P + tb - 1) / tb;
+  k_setup<<<gb, tb, 0, st>>>(cam, *mp, *ws, Zdepth, mask, min_sdf, P);
+  k_append_origin<<<1, 1, 0, st>>>(*ws, S + 1);
+  DIST_CHECK_CUDA(cudaGetLastError());
+  const int gu = min(gb, 4 * num_sms());
+  for (int s = 0; s < S; ++s) {
+    MlpArgs a{};
+    a.points = ws->pts + (size_t)(s & 1) * (size_t)(P + 1) * 3; a.n_host = P + (s == 0 ? 1 : 0);
+    a.n_dev = ws->counts + (s == 0 ? S + 1 : s);
+    a.clamp_dist = 0.f; a.sdf = ws->sdf; a.rows_evaluated = rows_eval;
+    rc = mlp_launch(net, nd, engine, 0, a, st);
+    if (rc) return rc;
+    k_march_update<<<gu, tb, 0, st>>>(cam, *mp, *ws, s, P);
+  }
+  k_finalize<<<gb, tb, 0, st>>>(*mp, *ws, Zdepth, mask, min_sdf, P);
+  DIST_CHECK_CUDA(cudaGetLastError());
+  return DIST_OK;
+}
+
+int render_normal_fwd(const dist_net_t* net, int engine, const dist_camera_t* camh, const float* Zdepth,
+                      const uint8_t* mask, float clamp_dist, int normalize, float* Znormal, int32_t* s_idx,
+                      float* s_pts, float* s_grad, int32_t* s_count, int64_t* rows_eval, cudaStream_t st) {
+  Cam cam;
+  int rc = make_cam(camh, &cam);
+  if (rc) return rc;
+  NetDev nd;
+  rc = make_netdev(net, &nd);
+  if (rc) return rc;
+  const int P = cam.W * cam.n_rows;
+  DIST_CHECK_CUDA(cudaMemsetAsync(s_count, 0, sizeof(int32_t), st));
+  DIST_CHECK_CUDA(cudaMemsetAsync(Znormal, 0, sizeof(float) * 3 * (size_t)P, st));
+  const int tb = 256, gb = (P + tb - 1) / tb;
+  k_normal_gen<<<gb, tb, 0, st>>>(cam, Zdepth, mask, s_idx, s_pts, s_count, P);
+  MlpArgs a{};
+  a.points = s_pts; a.n_host = P; a.n_dev = s_count; a.clamp_dist = clamp_dist; a.grad = s_grad;
+  a.rows_evaluated = rows_eval;
+  rc = mlp_launch(net, nd, engine, 1, a, st);
+  if (rc) return rc;
+  k_normal_finish<<<min(gb, 4 * num_sms()), tb, 0, st>>>(cam, s_idx, s_grad, s_count, normalize, Znormal, P);
+  DIST_CHECK_CUDA(cudaGetLastError());
+  return DIST_OK;
+}
+
+int render_depth_bwd(const dist_net_t* net, int engine, const dist_camera_t* camh, const dist_march_t* mp,
+                     const dist_workspace_t* ws, const float* gZ, const float* gM, float* acc0, float* accl,
+                     float* d_cam, float* d_ray, int32_t* s_row_pix, float* s_pts, float* s_coef, uint8_t* s_clamp,
+                     float* s_dpts, int32_t* s_count, int64_t* rows_eval, cudaStream_t st) {
+  (void)s_clamp;
+  Cam cam;
+  int rc = make_cam(camh, &cam);
+  if (rc) return rc;
+  NetDev nd;
+  rc = make_netdev(net, &nd);
+  if (rc) return rc;
+  const int P = cam.W * cam.n_rows;
+  DIST_CHECK_CUDA(cudaMemsetAsync(s_count, 0, sizeof(int32_t), st));
+  const int tb = 256, gb = (P + tb - 1) / tb;
+  k_bwd_gen<<<gb, tb, 0, st>>>(*mp, *ws, gZ, gM, s_row_pix, s_pts, s_coef, s_count, P);
+  MlpArgs a{};
+  a.points = s_pts; a.n_host = (int64_t)P * mp->buffer_size; a.n_dev = s_count; a.clamp_dist = 0.f;
+  a.grad = s_dpts; a.coef = s_coef; a.acc0 = acc0; a.accl = accl; a.rows_evaluated = rows_eval;
+  rc = mlp_launch(net, nd, engine, 2, a, st);
+  if (rc) return rc;
+  if (d_cam && d_ray) {
+    k_bwd_scatter<<<min((int)(((int64_t)P * mp->buffer_size + tb - 1) / tb), 4 * num_sms()), tb, 0, st>>>(
+        cam, *ws, s_row_pix, s_dpts, s_count, d_cam, d_ray, P);
+  }
+  DIST_CHECK_CUDA(cudaGetLastError());
+  return DIST_OK;
+}
+
+}  // namespace dist

@@ -1,0 +1,360 @@
+"""SDFRenderer -- drop-in for core/sdfrenderer/renderer.py:12-999 on the B200 engines.
+
+Same constructor and method signatures as the reference class; ``render_depth`` / ``render_normal`` / ``render``
+return tensors with the reference's shapes, dtypes and autograd connectivity (to ``latent``, ``R``, ``T`` according
+to the ``no_grad_*`` flags).  Everything per-ray runs in libdist_b200.so; PyTorch here only allocates buffers,
+launches on the current stream and chains the tiny camera Jacobian (c = -R^T T, ray = normalize(R^T K^-1 u)).
+
+Differences from the reference, all loud:
+  * no CPU path: ``use_gpu=False`` or a CPU decoder raises;
+  * ``ray_marching_type='pyramid_recursive'``, ``use_depth2normal``, ``num_forward_sampling``
+    and ``sample_index_type != 'min_abs'`` raise NotImplementedError;
+  * 3x4 ``transform_matrix`` raises (the reference's own 3x4 inverse path calls an un-imported ``pdb``);
+  * when no ray meets the unit sphere the reference dies inside ``.max()`` of an empty tensor; here
+    ``ValueError('No valid depth.')`` (renderer.py:215) is raised;
+  * new: ``render_silhouette`` = the (mask, min_abs_query) pair; ``rows=(row0, row_step, n_rows)`` renders a band
+    of image rows for ray-tile sharding across GPUs (parallel.py).
+"""
+import numpy as np
+import torch
+
+from . import _abi
+from .functional import resolve_engine, DEFAULT_ENGINE
+from .plan import plan_for
+
+_MARCH = {"trivial": _abi.MARCH_TRIVIAL, "trivial_non_parallel": _abi.MARCH_TRIVIAL,
+          "recursive": _abi.MARCH_RECURSIVE}
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+class _RenderDepthFn(torch.autograd.Function):
+    """Forward: dist_render_depth_fwd.  Backward: dist_render_depth_bwd + host camera chain."""
+
+    @staticmethod
+    def forward(ctx, latent, R, T, ren, opts):
+        lib, st = _abi.lib(), _stream()
+        plan = ren.plan
+        plan.refresh()
+        dev = ren.device
+        P, B = ren.P, ren.buffer_size
+        engine = resolve_engine(plan, opts["engine"])
+        if engine == _abi.ENGINE_TC:
+            from . import tc
+            tc.prepare(plan)
+        b0, bl, _ = plan.fold(latent, st)
+        net = plan.c_net(b0, bl)
+        Rd = R.detach().float().contiguous()
+        cam_pos = torch.matmul(-Rd.t(), T.detach().float()[:, None]).squeeze(1).contiguous()  # renderer.py:186
+        cam = ren._c_camera(Rd, cam_pos, opts["use_transform"])
+        mp = _abi.March(ren.march_step, B, _MARCH[opts["kind"]], 1 if opts["kind"] != "pyramid_recursive" else 0,
+                        ren.ray_marching_ratio, ren.threshold, float(opts["clamp_dist"]), 1 if opts["replay"] else 0)
+        f32 = dict(device=dev, dtype=torch.float32)
+        saved = {
+            "flags": torch.empty(P, device=dev, dtype=torch.uint8), "nreal": torch.empty(P, device=dev, dtype=torch.int32),
+            "top_sdf": torch.empty(B, P, **f32), "top_pt": torch.empty(B, 3, P, **f32),
+            "top_zafter": torch.empty(B, P, **f32), "top_zgen": torch.empty(B, P, **f32),
+            "sdf_origin": torch.empty(1, **f32), "dist": torch.empty(P, **f32),
+        }
+        scr = ren._scratch()
+        ws = _abi.Workspace()
+        for name in _abi.WS_FIELDS:
+            t = saved.get(name, scr.get(name))
+            setattr(ws, name, t.data_ptr())
+        Zdepth = torch.empty(P, **f32)
+        mask = torch.empty(P, device=dev, dtype=torch.uint8)
+        min_sdf = torch.empty(P, **f32)
+        _abi.check(lib.dist_render_depth_fwd(net, engine, cam, mp, ws, _abi.ptr(Zdepth), _abi.ptr(mask),
+                                             _abi.ptr(min_sdf), _abi.ptr(ren.rows_evaluated), st))
+        ren._last_counts = scr["counts"]
+        ctx.ren, ctx.opts, ctx.engine, ctx.mp = ren, opts, engine, mp
+        ctx.saved = saved
+        ctx.save_for_backward(latent, Rd, T.detach().float())
+        hit = saved["flags"].bitwise_and(1).bool()
+        ctx.mark_non_differentiable(mask, hit)
+        return Zdepth, mask, min_sdf, hit, saved["dist"]
+
+    @staticmethod
+    def backward(ctx, gZ, _gmask, gM, _ghit, _gdist):
+        latent, Rd, Td = ctx.saved_tensors
+        ren, opts, lib, st = ctx.ren, ctx.opts, _abi.lib(), _stream()
+        plan, dev, P, B = ren.plan, ren.device, ren.P, ren.buffer_size
+        b0, bl, _ = plan.fold(latent, st)
+        net = plan.c_net(b0, bl)
+        cam_pos = torch.matmul(-Rd.t(), Td[:, None]).squeeze(1).contiguous()
+        cam = ren._c_camera(Rd, cam_pos, opts["use_transform"])
+        scr = ren._scratch()
+        ws = _abi.Workspace()
+        for name in _abi.WS_FIELDS:
+            t = ctx.saved.get(name, scr.get(name))
+            setattr(ws, name, t.data_ptr())
+        gZ = gZ.contiguous().float() if (gZ is not None and opts["want_depth_grad"]) else None
+        gM = gM.contiguous().float() if (gM is not None and opts["want_mask_grad"]) else None
+        want_cam = opts["want_camera_grad"] and (ctx.needs_input_grad[1] or ctx.needs_input_grad[2])
+        f32 = dict(device=dev, dtype=torch.float32)
+        acc0 = torch.zeros(plan.bias[0].numel(), **f32)
+        accl = torch.zeros(plan.bias[plan.latent_in].numel(), **f32) if plan.latent_in >= 0 else None
+        d_cam = torch.zeros(3, **f32) if want_cam else None
+        d_ray = torch.zeros(3, P, **f32) if want_cam else None
+        g_lat = g_R = g_T = None
+        if gZ is not None or gM is not None:
+            rows = P * B
+            s_row = torch.empty(rows, device=dev, dtype=torch.int32)
+            s_pts = torch.empty(rows, 3, **f32)
+            s_coef = torch.empty(rows, **f32)
+            s_dpts = torch.empty(rows, 3, **f32)
+            s_cnt = torch.empty(1, device=dev, dtype=torch.int32)
+            _abi.check(lib.dist_render_depth_bwd(net, ctx.engine, cam, ctx.mp, ws, _abi.ptr(gZ), _abi.ptr(gM),
+                                                 _abi.ptr(acc0), _abi.ptr(accl), _abi.ptr(d_cam), _abi.ptr(d_ray),
+                                                 _abi.ptr(s_row), _abi.ptr(s_pts), _abi.ptr(s_coef), None,
+                                                 _abi.ptr(s_dpts), _abi.ptr(s_cnt), _abi.ptr(ren.rows_evaluated), st))
+            if ctx.needs_input_grad[0] and latent is not None:
+                g_lat = plan.latent_grad(acc0, accl).reshape(latent.shape).to(latent.dtype)
+            if want_cam:
+                with torch.enable_grad():
+                    Rg, Tg = Rd.clone().requires_grad_(True), Td.clone().requires_grad_(True)
+                    c = torch.matmul(-Rg.t(), Tg[:, None]).squeeze(1)
+                    rays = ren.get_camera_rays(Rg)
+                    g_R, g_T = torch.autograd.grad([c, rays], [Rg, Tg], [d_cam, d_ray], allow_unused=True)
+        return g_lat, g_R, g_T, None, None
+
+
+class SDFRenderer(object):
+    def __init__(self, decoder, intrinsic, img_hw=None, transform_matrix=None, march_step=50, buffer_size=5,
+                 ray_marching_ratio=1.5, use_depth2normal=False, max_sample_dist=0.2, radius=1.0, threshold=5e-5,
+                 scale_list=[4, 2, 1], march_step_list=[3, 3, -1], use_gpu=True, is_eval=True, engine=None,
+                 rows=None):
+        # renderer.py:13-59
+        self.decoder = decoder
+        if use_gpu and torch.cuda.device_count() == 0:
+            raise ValueError('No GPU device found.')  # renderer.py:51-52
+        if not use_gpu:
+            raise RuntimeError("dist-renderer_b200 has no CPU path: use_gpu=False is not supported")
+        p = next(self.decoder.parameters())
+        if not p.is_cuda:
+            raise ValueError("the decoder must be on a CUDA device (no CPU path)")
+        self.device = p.device
+        if is_eval:
+            self.decoder.eval()
+        if not (1 <= buffer_size <= _abi.MAX_BUFFER):
+            raise NotImplementedError("buffer_size must be in [1, %d]" % _abi.MAX_BUFFER)
+        self.march_step, self.buffer_size = int(march_step), int(buffer_size)
+        self.max_sample_dist = max_sample_dist
+        self.ray_marching_ratio = float(ray_marching_ratio)
+        self.use_depth2normal = use_depth2normal
+        self.radius, self.threshold = float(radius), float(threshold)
+        self.scale_list, self.march_step_list = scale_list, march_step_list
+        self.engine = engine or DEFAULT_ENGINE
+        if type(intrinsic) == torch.Tensor:
+            intrinsic = intrinsic.detach().cpu().numpy()
+        self.intrinsic = np.asarray(intrinsic, dtype=np.float64)
+        if img_hw is None:
+            img_hw = (int(self.intrinsic[1, 2] * 2), int(self.intrinsic[0, 2] * 2))
+        self.img_hw = (int(img_hw[0]), int(img_hw[1]))
+        h, w = self.img_hw
+        self.rows = (0, 1, h) if rows is None else tuple(int(v) for v in rows)
+        row0, step, n_rows = self.rows
+        if not (0 <= row0 and step >= 1 and n_rows >= 1 and row0 + (n_rows - 1) * step < h):
+            raise ValueError("rows=(row0,row_step,n_rows) outside the image")
+        self.local_hw = (n_rows, w)
+        self.P = n_rows * w
+        self.K = torch.from_numpy(self.intrinsic).float().to(self.device)
+        self.K_inv = torch.from_numpy(np.linalg.inv(self.intrinsic)).float().to(self.device)
+        if transform_matrix is None:
+            transform_matrix = np.array([[1., 0., 0.], [0., 0., -1.], [0., 1., 0.]])
+        transform_matrix = np.asarray(transform_matrix, dtype=np.float64)
+        if transform_matrix.shape != (3, 3):
+            raise NotImplementedError("only 3x3 transform_matrix is supported (renderer.py:116 is dead code upstream)")
+        self.transform_matrix = torch.from_numpy(transform_matrix).float().to(self.device)
+        self.plan = plan_for(decoder)
+        self.rows_evaluated = torch.zeros(1, device=self.device, dtype=torch.int64)
+        self._homo_calib = None
+        self._calib_map = None
+        self._scr = None
+        self._last_counts = None
+
+    # ---- accessors of the reference ------------------------------------------------------------------------
+    def get_intrinsic(self):
+        return self.intrinsic
+
+    def get_threshold(self):
+        return self.threshold
+
+    def get_img_hw(self):
+        return self.img_hw
+
+    @property
+    def homo_calib(self):
+        """K^-1 [x, y, 1] for the rendered rows, (3, P).  renderer.py:37-39."""
+        if self._homo_calib is None:
+            row0, step, n_rows = self.rows
+            w = self.img_hw[1]
+            ys = (row0 + step * torch.arange(n_rows, device=self.device)).float()
+            xs = torch.arange(w, device=self.device).float()
+            Y, X = torch.meshgrid(ys, xs, indexing="ij")
+            homo = torch.stack([X.reshape(-1), Y.reshape(-1), torch.ones(self.P, device=self.device)], 0)
+            self._homo_calib = torch.matmul(self.K_inv, homo)
+        return self._homo_calib
+
+    @property
+    def calib_map(self):
+        if self._calib_map is None:
+            self._calib_map = self.normalize_vectors(self.homo_calib)[2, :]  # renderer.py:59
+        return self._calib_map
+
+    def normalize_vectors(self, x):  # renderer.py:171-178
+        return x.div(torch.norm(x, p=2, dim=0).expand_as(x) + 1e-12)
+
+    def get_camera_location(self, R, T):  # renderer.py:180-188
+        return torch.matmul(-R.transpose(1, 0), T[:, None]).squeeze(1)
+
+    def get_camera_rays(self, R, homo=None):  # renderer.py:190-200
+        return self.normalize_vectors(torch.matmul(R.transpose(1, 0), self.homo_calib if homo is None else homo))
+
+    def transform_points(self, points):  # renderer.py:84-98
+        return torch.matmul(self.transform_matrix, points)
+
+    def inv_transform_points(self, points):  # renderer.py:100-120
+        return torch.matmul(self.transform_matrix.transpose(1, 0), points)
+
+    def generate_point_samples(self, cam_pos, cam_rays, Zdepth, inv_transform=True, has_zdepth_grad=False):
+        # renderer.py:202-223 (host-side helper kept for subclasses; the march generates its points in-kernel)
+        if not has_zdepth_grad:
+            Zdepth = Zdepth.detach()
+        if Zdepth.shape[0] == 0:
+            raise ValueError('No valid depth.')
+        points = cam_rays * Zdepth[None, :] + cam_pos[:, None]
+        if inv_transform:
+            points = self.inv_transform_points(points)
+        if not points.requires_grad:
+            points.requires_grad = True
+        return points
+
+    def get_distance_from_origin(self, cam_pos, cam_rays):  # renderer.py:225-239
+        ptq = (cam_pos[:, None] * cam_rays).sum(0)
+        return torch.norm(cam_pos[:, None] - ptq[None, :] * cam_rays, p=2, dim=0)
+
+    # ---- internals ------------------------------------------------------------------------------------------
+    def _c_camera(self, R, cam_pos, use_transform=True):
+        cam = _abi.Camera()
+        Kinv = np.linalg.inv(self.intrinsic).astype(np.float32).reshape(-1)
+        M = self.transform_matrix.detach().cpu().numpy().reshape(-1) if use_transform else np.eye(3).reshape(-1)
+        for i in range(9):
+            cam.Kinv[i], cam.M[i] = float(Kinv[i]), float(M[i])
+        cam._keep = (R, cam_pos)
+        cam.R, cam.cam_pos = R.data_ptr(), cam_pos.data_ptr()
+        cam.width, cam.height = self.img_hw[1], self.img_hw[0]
+        cam.row0, cam.row_step, cam.n_rows = self.rows
+        cam.radius = self.radius
+        return cam
+
+    def _scratch(self):
+        """Reusable (not saved-for-backward) per-renderer device scratch, stream-ordered."""
+        if self._scr is None:
+            P, dev = self.P, self.device
+            f32 = dict(device=dev, dtype=torch.float32)
+            i32 = dict(device=dev, dtype=torch.int32)
+            self._scr = {
+                "ray": torch.empty(3, P, **f32), "entry": torch.empty(P, **f32), "exit_": torch.empty(P, **f32),
+                "z": torch.empty(P, **f32), "list_a": torch.empty(P, **i32), "list_b": torch.empty(P, **i32),
+                "pts": torch.empty(2, P + 1, 3, **f32), "sdf": torch.empty(P + 1, **f32),
+                "counts": torch.empty(self.march_step + 2, **i32),
+                "n_idx": torch.empty(P, **i32), "n_pts": torch.empty(P, 3, **f32), "n_grad": torch.empty(P, 3, **f32),
+                "n_cnt": torch.empty(1, **i32),
+            }
+        return self._scr
+
+    def reset_row_counter(self):
+        self.rows_evaluated.zero_()
+
+    # ---- rendering --------------------------------------------------------------------------------------------
+    def render_depth(self, latent, R, T, clamp_dist=0.1, sample_index_type='min_abs', profile=False, no_grad=False,
+                     no_grad_depth=False, no_grad_mask=False, no_grad_camera=False, ray_marching_type='recursive',
+                     use_transform=True, check_empty=True):
+        """(Zdepth[P], valid_mask[P] bool, min_sdf[P]) -- renderer.py:836-878."""
+        if no_grad:
+            no_grad_depth, no_grad_mask, no_grad_camera = True, True, True
+        if sample_index_type != 'min_abs':
+            raise NotImplementedError("sample_index_type='%s' is not implemented (only 'min_abs')" % sample_index_type)
+        if ray_marching_type == 'pyramid_recursive':
+            raise NotImplementedError("ray_marching_type='pyramid_recursive' is not implemented yet "
+                                      "(use 'recursive' or 'trivial')")
+        if ray_marching_type not in _MARCH:
+            raise ValueError('Error! Invalid type of ray marching: {}.'.format(ray_marching_type))  # renderer.py:834
+        any_grad = torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (latent, R, T))
+        opts = dict(kind=ray_marching_type, clamp_dist=clamp_dist, use_transform=use_transform, engine=self.engine,
+                    want_depth_grad=any_grad and not no_grad_depth, want_mask_grad=any_grad and not no_grad_mask,
+                    want_camera_grad=any_grad and not no_grad_camera, replay=not no_grad_depth)
+        Zdepth, mask, min_sdf, hit, dist = _RenderDepthFn.apply(latent, R, T, self, opts)
+        if check_empty and int(self._last_counts[0].item()) == 0:
+            raise ValueError('No valid depth.')  # renderer.py:214-215
+        if torch.is_grad_enabled() and (R.requires_grad or T.requires_grad):
+            # renderer.py:842,863: the fill of rays missing the unit sphere stays differentiable w.r.t. the camera
+            cam_pos = self.get_camera_location(R, T)
+            d = self.get_distance_from_origin(cam_pos, self.get_camera_rays(R))
+            min_sdf = torch.where(hit, min_sdf, d + self.threshold - self.radius)
+        if no_grad_depth:
+            Zdepth = Zdepth.detach()
+        if no_grad_mask and not (R.requires_grad or T.requires_grad):
+            min_sdf = min_sdf.detach()
+        return Zdepth, mask.bool(), min_sdf
+
+    def render_normal(self, latent, R, T, Zdepth, valid_mask, clamp_dist=0.1, MAX_POINTS=100000, no_grad=False,
+                      normalize=True, use_transform=True):
+        """Znormal (3, P): analytic decoder input-gradient at the hit points -- renderer.py:880-910.
+
+        The gradient of a ReLU / weight-norm decoder is piecewise constant, so the reference's autograd path
+        through this tensor to latent / T is zero; the returned tensor carries no graph."""
+        lib, st = _abi.lib(), _stream()
+        plan = self.plan
+        plan.refresh()
+        engine = resolve_engine(plan, self.engine)
+        if engine == _abi.ENGINE_TC:
+            from . import tc
+            tc.prepare(plan)
+        b0, bl, _ = plan.fold(latent, st)
+        net = plan.c_net(b0, bl)
+        Rd = R.detach().float().contiguous()
+        cam_pos = torch.matmul(-Rd.t(), T.detach().float()[:, None]).squeeze(1).contiguous()
+        cam = self._c_camera(Rd, cam_pos, use_transform)
+        scr = self._scratch()
+        Zd = Zdepth.detach().float().contiguous()
+        m8 = valid_mask.detach().to(torch.uint8).contiguous()
+        Znormal = torch.empty(3, self.P, device=self.device, dtype=torch.float32)
+        _abi.check(lib.dist_render_normal_fwd(net, engine, cam, _abi.ptr(Zd), _abi.ptr(m8), float(clamp_dist),
+                                              1 if normalize else 0, _abi.ptr(Znormal), _abi.ptr(scr["n_idx"]),
+                                              _abi.ptr(scr["n_pts"]), _abi.ptr(scr["n_grad"]), _abi.ptr(scr["n_cnt"]),
+                                              _abi.ptr(self.rows_evaluated), st))
+        return Znormal
+
+    def render(self, latent, R, T, clamp_dist=0.1, sample_index_type='min_abs', profile=False, no_grad=False,
+               no_grad_depth=False, no_grad_normal=False, no_grad_mask=False, no_grad_camera=False,
+               normalize_normal=True, use_transform=True, ray_marching_type='pyramid_recursive',
+               num_forward_sampling=0):
+        """(depth[h,w], normal[h,w,3], mask[h,w] uint8, min_abs_query[h,w]) -- renderer.py:943-999."""
+        if no_grad:
+            no_grad_depth, no_grad_normal, no_grad_mask, no_grad_camera = True, True, True, True
+        if self.use_depth2normal:
+            raise NotImplementedError("use_depth2normal is outside the fused path")
+        if num_forward_sampling != 0:
+            raise NotImplementedError("num_forward_sampling is not implemented")
+        h, w = self.local_hw
+        Zdepth, valid_mask, min_abs_query = self.render_depth(
+            latent, R, T, clamp_dist=clamp_dist, sample_index_type=sample_index_type, profile=profile, no_grad=no_grad,
+            no_grad_depth=no_grad_depth, no_grad_mask=no_grad_mask, no_grad_camera=no_grad_camera,
+            ray_marching_type=ray_marching_type, use_transform=use_transform)
+        depth = torch.where(valid_mask, Zdepth * self.calib_map, torch.full_like(Zdepth, 1e11))  # renderer.py:967-969
+        normal = self.render_normal(latent, R, T, Zdepth, valid_mask, clamp_dist=clamp_dist, no_grad=no_grad_normal,
+                                    normalize=normalize_normal, use_transform=use_transform)
+        normal = torch.matmul(R if not no_grad_normal else R.detach(), normal)  # renderer.py:978
+        normal = torch.cat([normal[:1] * (-1), normal[1:]], 0)                   # renderer.py:979
+        normal = normal.reshape(3, h, w).permute(1, 2, 0)
+        return depth.reshape(h, w), normal, valid_mask.reshape(h, w).type(torch.uint8), min_abs_query.reshape(h, w)
+
+    def render_silhouette(self, latent, R, T, **kw):
+        """(mask[h,w] uint8, min_abs_query[h,w]): the pair the reference uses as the silhouette (renderer.py:878,990)."""
+        h, w = self.local_hw
+        _, valid_mask, min_abs_query = self.render_depth(latent, R, T, **kw)
+        return valid_mask.reshape(h, w).type(torch.uint8), min_abs_query.reshape(h, w)

@@ -1,0 +1,188 @@
+/*
+ * dist_b200.h -- C ABI of the B200-native sphere-tracing library (libdist_b200.so).
+ *
+ * The reference (B1ueber2y/DIST-Renderer) has no FFI/plugin interface: its boundary is the Python class
+ * `SDFRenderer` (core/sdfrenderer/renderer.py:12) plus `decode_sdf` / `decode_sdf_gradient`
+ * (core/utils/decoder_utils.py:53,76) and `Decoder.inference` (core/graph/deep_sdf_decoder.py:80).
+ * Each entry point below names the reference code it replaces.  Conventions:
+ *   - every pointer is a DEVICE pointer owned by the caller (torch allocates; the library never allocates,
+ *     never synchronises the device and never touches the host copy of any buffer), except `dist_net_t*`
+ *     / `dist_camera_t*` descriptors, which are small host structs passed by pointer and copied at launch;
+ *   - all work is enqueued on the `stream` argument (a cudaStream_t passed as void*);
+ *   - return value 0 = success, otherwise a DIST_E_* code; dist_last_error() gives the message;
+ *   - all floating-point data is fp32, row-major.
+ */
+#ifndef DIST_B200_H_
+#define DIST_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DIST_ABI_VERSION 1
+#define DIST_MAX_LAYERS 16
+#define DIST_MAX_WIDTH 512
+#define DIST_MAX_BUFFER 8      /* max buffer_size (samples kept per ray) */
+
+enum {
+  DIST_OK = 0,
+  DIST_E_INVALID = 1,    /* bad argument / unsupported network shape */
+  DIST_E_CUDA = 2,       /* a CUDA runtime call failed */
+  DIST_E_UNSUPPORTED = 3 /* feature not available in this build (e.g. tensor path on a non-sm_100 device) */
+};
+
+enum { DIST_MARCH_TRIVIAL = 0, DIST_MARCH_RECURSIVE = 1 };
+
+/* Evaluation engines for the decoder rows. */
+enum {
+  DIST_ENGINE_SIMT = 0,   /* fp32 FFMA reference engine (exact fp32 arithmetic, CUDA cores) */
+  DIST_ENGINE_TC = 1      /* tcgen05 tensor-core engine, split-fp16 operands with fp32 accumulation */
+};
+
+/*
+ * The decoder network in "folded" form (deep_sdf_decoder.py:80-111 with weight-norm applied and the latent code
+ * folded into per-render biases -- SURVEY.md section 7 step 2):
+ *   layer 0 takes xyz (K=3); the layer listed in `latent_in` takes [h | xyz] (K = width of h + 3);
+ *   every other layer takes the previous activation.  ReLU after all but the last layer, tanh at the end
+ *   (twice when `use_tanh`).  The last layer must have N = 1.
+ * Wt[l] : [Kp8][Np4] fp32, transposed weights (input-major), zero padded: Kp8 = roundup(K,8), Np4 = roundup(N,4).
+ * W [l] : [Np8][Kp4] fp32, weights (output-major), zero padded.
+ * bias[l]: [Np4] fp32.  For layer 0 and the latent_in layer this is the per-render folded bias written by
+ *          dist_fold_latent(); for the others the plain bias.
+ * Wz0 / Wzl : latent columns of layer 0 / the latent_in layer, [N][latent_size], used by dist_fold_latent().
+ */
+typedef struct dist_net {
+  int32_t n_layers;
+  int32_t latent_size;
+  int32_t latent_in;          /* layer index, or -1 */
+  int32_t use_tanh;
+  int32_t K[DIST_MAX_LAYERS];
+  int32_t N[DIST_MAX_LAYERS];
+  const float* Wt[DIST_MAX_LAYERS];
+  const float* W[DIST_MAX_LAYERS];
+  const float* bias[DIST_MAX_LAYERS];
+  const float* Wz0;
+  const float* b0;            /* unfolded bias of layer 0, [N0] */
+  const float* Wzl;
+  const float* bl;            /* unfolded bias of the latent_in layer */
+  /* tensor-core engine operands (NULL when only the SIMT engine is prepared) */
+  const void* tc_blob;        /* split-fp16 weight tiles, see csrc/mlp_tc.cu */
+  const float* tc_scale;      /* per-layer power-of-two operand scales */
+  int64_t tc_blob_bytes;
+} dist_net_t;
+
+/* Camera + image description for one render (renderer.py:13-59,180-200). */
+typedef struct dist_camera {
+  float Kinv[9];              /* inverse intrinsic, row-major (renderer.py:161-164) */
+  float M[9];                 /* transform_matrix, row-major (renderer.py:44-48); only 3x3 supported */
+  const float* R;             /* device, [9] row-major world->camera rotation */
+  const float* cam_pos;       /* device, [3]  = -R^T T  (renderer.py:180-188) */
+  int32_t width;              /* full image width */
+  int32_t height;             /* full image height */
+  int32_t row0;               /* first image row rendered by this call (ray-tile sharding) */
+  int32_t row_step;           /* stride between rendered rows (interleaved bands) */
+  int32_t n_rows;             /* number of rows rendered; local pixel lp = lrow*width + x */
+  float radius;               /* unit-sphere radius (renderer.py:23) */
+} dist_camera_t;
+
+/* March parameters (renderer.py:13 ctor arguments + render_depth arguments). */
+typedef struct dist_march {
+  int32_t march_step;
+  int32_t buffer_size;
+  int32_t marching_type;      /* DIST_MARCH_* */
+  int32_t first_query_check;  /* renderer.py:580-582 */
+  float ratio;                /* ray_marching_ratio */
+  float threshold;
+  float clamp_dist;
+  int32_t replay_grad_rounding; /* 1: reproduce the value-neutral (z - a) + a roundings of renderer.py:414-417 */
+} dist_march_t;
+
+/*
+ * Per-render device workspace, all arrays sized by the number of local pixels P = n_rows*width
+ * (B = buffer_size).  The top-B sample records double as the tensors saved for backward.
+ */
+typedef struct dist_workspace {
+  float* ray;        /* [3][P] unit ray directions, world frame */
+  float* entry;      /* [P] ray depth of the unit-sphere entry (renderer.py:254-273) */
+  float* exit_;      /* [P] entry + chord (renderer.py:275-282) */
+  float* dist;       /* [P] distance of the ray to the origin */
+  float* z;          /* [P] marching depth relative to entry */
+  uint8_t* flags;    /* [P] bit0 sphere hit, bit1 first query > threshold, bit2 was live in the last executed step */
+  int32_t* nreal;    /* [P] number of real samples recorded */
+  float* top_sdf;    /* [B][P] samples with the smallest |sdf|, sorted ascending */
+  float* top_pt;     /* [B][3][P] their points (decoder frame) */
+  float* top_zafter; /* [B][P] marching depth after the step that produced the sample */
+  float* top_zgen;   /* [B][P] absolute ray depth the sample point was generated at (NaN: not on this ray) */
+  int32_t* list_a;   /* [P] active ray list (ping) */
+  int32_t* list_b;   /* [P] active ray list (pong) */
+  float* pts;        /* [2][P+1][3] query points, ping-pong by step parity (+1: the origin row of step 0) */
+  float* sdf;        /* [P+1] decoder outputs of the current step */
+  int32_t* counts;   /* [march_step + 2] active rays per step; zeroed by dist_render_depth_fwd */
+  float* sdf_origin; /* [1] sdf at the origin (filler samples, renderer.py:539-540) */
+} dist_workspace_t;
+
+/* ---- library ---- */
+int dist_abi_version(void);
+const char* dist_last_error(void);
+/* 1 if the device has the tcgen05 path (compute capability 10.x) */
+int dist_device_supports_tc(int device);
+
+/* ---- decoder (decoder_utils.py:53-92, deep_sdf_decoder.py:80-111) ---- */
+
+/* Per-render folded biases: out0[n] = b0[n] + Wz0[n,:].latent ; outl likewise for the latent_in layer.
+ * Replaces the latent.expand + torch.cat of decoder_utils.py:61-62 and deep_sdf_decoder.py:92-93. */
+int dist_fold_latent(const dist_net_t* net, const float* latent, float* out0, float* outl, void* stream);
+
+/* sdf[i] = decoder(latent, points[i]) for i < n (n read from *n_dev when n_dev != NULL, else n_host).
+ * clamp_dist <= 0 means no clamp.  Replaces decode_sdf (decoder_utils.py:53-74). */
+int dist_decoder_forward(const dist_net_t* net, int engine, const float* points, int64_t n_host,
+                         const int32_t* n_dev, float clamp_dist, float* sdf, void* stream);
+
+/* grad[i] = d clamp(sdf)/d xyz at points[i]; sdf (optional) receives the clamped value.
+ * Replaces decode_sdf_gradient (decoder_utils.py:76-92). */
+int dist_decoder_input_grad(const dist_net_t* net, int engine, const float* points, int64_t n_host,
+                            const int32_t* n_dev, float clamp_dist, float* grad, float* sdf, void* stream);
+
+/* Backward replay: for row i with upstream coefficient coef[i] on its (optionally clamped) sdf,
+ *   dpoints[i] = coef[i] * d sdf/d xyz,   acc0 += sum_i coef[i] * d sdf/d preact0,  accl += ... latent_in layer.
+ * use_clamp[i] != 0 applies the clamp mask.  acc0/accl ([N0]/[Nl] fp32) are accumulated atomically (caller zeroes).
+ * Replaces the autograd backward of the re-query decoder calls (renderer.py:386,415; optimize_single.py:83). */
+int dist_decoder_backward(const dist_net_t* net, int engine, const float* points, const float* coef,
+                          const uint8_t* use_clamp, int64_t n_host, const int32_t* n_dev, float clamp_dist,
+                          float* dpoints, float* acc0, float* accl, void* stream);
+
+/* ---- renderer (renderer.py:836-910) ---- */
+
+/* Ray setup + sphere clip + march + sample selection + depth/mask/min-sdf maps for the rows of `cam`.
+ * Outputs (local pixel order): Zdepth[P] (1e11 where the ray misses the unit sphere), mask[P] (uint8),
+ * min_sdf[P] (dist + threshold - radius where the ray misses the unit sphere), rows_evaluated[1] (int64 counter of
+ * decoder rows pushed through the network, for roofline accounting).  Replaces render_depth forward
+ * (renderer.py:836-878) with ray_marching_trivial / ray_marching_recursive (renderer.py:472-583). */
+int dist_render_depth_fwd(const dist_net_t* net, int engine, const dist_camera_t* cam, const dist_march_t* mp,
+                          const dist_workspace_t* ws, float* Zdepth, uint8_t* mask, float* min_sdf,
+                          int64_t* rows_evaluated, void* stream);
+
+/* Surface normals at Zdepth on `mask` pixels: Znormal[3][P], zeros elsewhere.  Replaces render_normal
+ * (renderer.py:880-910) with the analytic decoder input-gradient (decoder_utils.py:76-92).
+ * scratch_idx[P] int32, scratch_pts[P][3], scratch_grad[P][3], scratch_count[1] int32 are caller workspaces. */
+int dist_render_normal_fwd(const dist_net_t* net, int engine, const dist_camera_t* cam, const float* Zdepth,
+                           const uint8_t* mask, float clamp_dist, int normalize, float* Znormal,
+                           int32_t* scratch_idx, float* scratch_pts, float* scratch_grad, int32_t* scratch_count,
+                           int64_t* rows_evaluated, void* stream);
+
+/* Backward of dist_render_depth_fwd for upstream gZ[P] (on Zdepth) and gM[P] (on min_sdf; only sphere-hit pixels are
+ * used): replays the saved top-B sample points.  Outputs acc0/accl as in dist_decoder_backward, d_cam_pos[3] and
+ * d_ray[3][P] (gradient w.r.t. camera centre and per-pixel unit ray, for the host-side camera chain).
+ * Either gZ or gM may be NULL.  scratch_* hold the compacted replay rows: rows up to P*buffer_size. */
+int dist_render_depth_bwd(const dist_net_t* net, int engine, const dist_camera_t* cam, const dist_march_t* mp,
+                          const dist_workspace_t* ws, const float* gZ, const float* gM, float* acc0, float* accl,
+                          float* d_cam_pos, float* d_ray, int32_t* scratch_row_pix, float* scratch_pts,
+                          float* scratch_coef, uint8_t* scratch_clamp, float* scratch_dpts, int32_t* scratch_count,
+                          int64_t* rows_evaluated, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIST_B200_H_ */

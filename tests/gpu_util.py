@@ -1,0 +1,94 @@
+"""Helpers shared by the GPU parity tests."""
+import copy
+
+import numpy as np
+import torch
+
+import cases
+from oracle.sdf_oracle import OracleSDFRenderer
+
+pkg = cases.pkg
+
+
+def rel(a, b):
+    a = torch.as_tensor(a).detach().double().cpu()
+    b = torch.as_tensor(b).detach().double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-300))
+
+
+_GPU_DEC = {}
+
+
+def gpu_decoder(kind):
+    if kind not in _GPU_DEC:
+        _GPU_DEC[kind] = copy.deepcopy(cases.decoder(kind)).cuda()
+    return _GPU_DEC[kind]
+
+
+def run_gpu(cs, engine=None, grads=True, dec=None, dec_kind=None):
+    dev = torch.device("cuda")
+    dec = dec if dec is not None else gpu_decoder(dec_kind or cs["decoder"])
+    K, R, T = cases.camera(cs["cam"], cs["hw"])
+    ren = pkg.SDFRenderer(dec, K, img_hw=cs["hw"], march_step=cs["march_step"], buffer_size=cs["buffer_size"],
+                          engine=engine)
+    lat = cases.synth.make_latent(dec.latent_size).to(dev).requires_grad_(grads)
+    Rg, Tg = R.to(dev).requires_grad_(grads), T.to(dev).requires_grad_(grads)
+    out = ren.render(lat, Rg, Tg, ray_marching_type=cs["kind"], no_grad=not grads)
+    g = None
+    if grads:
+        cases.scalar_loss(out).backward()
+        g = (lat.grad.cpu(), Rg.grad.cpu(), Tg.grad.cpu())
+    return [o.detach().cpu() for o in out], g, ren
+
+
+def run_oracle(cs, grads=True, dec=None, dtype=torch.float32):
+    dec = dec if dec is not None else cases.decoder(cs["decoder"])
+    if dtype == torch.float64:
+        dec = copy.deepcopy(dec).double()
+    K, R, T = cases.camera(cs["cam"], cs["hw"])
+    ren = OracleSDFRenderer(dec, K, img_hw=cs["hw"], march_step=cs["march_step"], buffer_size=cs["buffer_size"],
+                            dtype=dtype)
+    lat = cases.synth.make_latent(dec.latent_size).to(dtype).requires_grad_(grads)
+    Rg, Tg = R.to(dtype).requires_grad_(grads), T.to(dtype).requires_grad_(grads)
+    out = ren.render(lat, Rg, Tg, ray_marching_type=cs["kind"], no_grad=not grads)
+    g = None
+    if grads:
+        cases.scalar_loss(out).backward()
+        g = (lat.grad, Rg.grad, Tg.grad)
+    return [o.detach() for o in out], g
+
+
+def normal_error(n_a, n_b, mask, outlier_frac=0.001, outlier_thresh=1e-3):
+    """rel-L2 of the normal map on `mask` after dropping at most outlier_frac pixels whose per-pixel error exceeds
+    outlier_thresh (ReLU-boundary flips: the fp32 reference vs its own fp64 twin shows the same).
+    Returns (rel_l2_without_outliers, n_outliers, n_allowed)."""
+    a = torch.as_tensor(n_a).double().reshape(-1, 3)[mask.reshape(-1)]
+    b = torch.as_tensor(n_b).double().reshape(-1, 3)[mask.reshape(-1)]
+    if a.shape[0] == 0:
+        return 0.0, 0, 0
+    err = (a - b).norm(dim=1)
+    bad = err > outlier_thresh
+    allowed = max(2, int(np.ceil(outlier_frac * a.shape[0])))
+    keep = ~bad
+    r = float((a[keep] - b[keep]).norm() / (b[keep].norm() + 1e-300))
+    return r, int(bad.sum()), allowed
+
+
+def compare(out, ref, g=None, gref=None, tol=1e-4, gtol=2e-3, max_xor=2):
+    """Asserts the parity bar of BASELINE.md section 3 and returns the measured numbers."""
+    m = out[2].bool() & ref[2].bool()
+    xor = int((out[2] != ref[2]).sum())
+    res = dict(xor=xor, hits=int(ref[2].sum()))
+    assert xor <= max_xor, res
+    if m.any():
+        res["depth"] = rel(out[0][m], ref[0][m])
+        assert res["depth"] < tol, res
+        res["normal"], res["n_out"], allowed = normal_error(out[1], ref[1], m)
+        assert res["normal"] < tol and res["n_out"] <= allowed, res
+    res["min_sdf"] = rel(out[3], ref[3])
+    assert res["min_sdf"] < tol, res
+    if g is not None:
+        for name, a, b in zip(("g_latent", "g_R", "g_T"), g, gref):
+            res[name] = rel(a, b)
+            assert res[name] < gtol, res
+    return res

@@ -1,0 +1,140 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and the golden fixtures.
+
+Tolerances (fp32 path): depth / min_sdf rel-L2 < 1e-4 on the mask intersection; mask XOR <= 2 pixels; normal
+rel-L2 < 1e-4 after excluding <= 0.1 % ReLU-flip outlier pixels; gradients rel-L2 < 2e-3.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import cases
+import gpu_util as gu
+
+pytestmark = pytest.mark.gpu
+pkg = cases.pkg
+RENDER_CASES = [n for n in sorted(cases.CASES) if cases.CASES[n]["kind"] != "pyramid_recursive"]
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _built():
+    import importlib
+    importlib.import_module("dist-renderer_b200.build").build()
+
+
+@pytest.mark.parametrize("engine", ["simt"])
+def test_decoder_points_golden(engine):
+    gold = np.load(os.path.join(cases.GOLDEN_DIR, "decoder_points.npz"))
+    dec = gu.gpu_decoder("B")
+    lat = cases.synth.make_latent().cuda()
+    pts = torch.from_numpy(gold["points"]).cuda()
+    sdf = pkg.decode_sdf(dec, lat, pts, clamp_dist=None, engine=engine)
+    assert sdf.shape == (pts.shape[0], 1)
+    assert gu.rel(sdf, gold["sdf"]) < 1e-5
+    assert float((sdf.cpu() - torch.from_numpy(gold["sdf"])).abs().max()) < 2e-6
+    grad = pkg.decode_sdf_gradient(dec, lat, pts, clamp_dist=0.1, engine=engine)
+    err = (grad.cpu() - torch.from_numpy(gold["grad"])).norm(dim=1)
+    assert int((err > 1e-3).sum()) <= 3          # ReLU-boundary flips
+    keep = err <= 1e-3
+    assert gu.rel(grad.cpu()[keep], torch.from_numpy(gold["grad"])[keep]) < 1e-5
+
+
+def test_decode_sdf_autograd():
+    """decode_sdf is differentiable w.r.t. latent and points like the reference's (decoder_utils.py:53)."""
+    from oracle.sdf_oracle import decode_sdf as o_decode
+    dec_c, dec_g = cases.decoder("B"), gu.gpu_decoder("B")
+    g = torch.Generator().manual_seed(3)
+    pts = (torch.rand(500, 3, generator=g) - 0.5) * 1.2
+    w = torch.randn(500, 1, generator=g)
+    lat_c = cases.synth.make_latent().requires_grad_(True)
+    p_c = pts.clone().requires_grad_(True)
+    (o_decode(dec_c, lat_c, p_c, clamp_dist=0.1) * w).sum().backward()
+    lat_g = cases.synth.make_latent().cuda().requires_grad_(True)
+    p_g = pts.cuda().requires_grad_(True)
+    (pkg.decode_sdf(dec_g, lat_g, p_g, clamp_dist=0.1, engine="simt") * w.cuda()).sum().backward()
+    assert gu.rel(lat_g.grad, lat_c.grad) < 1e-4
+    assert gu.rel(p_g.grad, p_c.grad) < 1e-4
+
+
+@pytest.mark.parametrize("name", RENDER_CASES)
+def test_render_matches_oracle_simt(name):
+    cs = cases.CASES[name]
+    out, g, ren = gu.run_gpu(cs, engine="simt")
+    ref, gref = gu.run_oracle(cs)
+    res = gu.compare(out, ref, g, gref)
+    print(name, res, "rows", int(ren.rows_evaluated.item()))
+
+
+@pytest.mark.parametrize("name", RENDER_CASES)
+def test_render_matches_golden_simt(name):
+    """Directly against the outputs of the unmodified reference stored in tests/golden."""
+    cs = cases.CASES[name]
+    gold = np.load(os.path.join(cases.GOLDEN_DIR, name + ".npz"))
+    out, g, _ = gu.run_gpu(cs, engine="simt")
+    ref = [torch.from_numpy(gold[k]) for k in ("depth", "normal", "mask", "min_sdf")]
+    gref = [torch.from_numpy(gold[k]) for k in ("g_latent", "g_R", "g_T")]
+    gu.compare(out, ref, g, gref)
+
+
+def test_render_depth_no_grad_matches_golden():
+    """no_grad render: the value-neutral (z-a)+a roundings are skipped exactly as renderer.py:410-411."""
+    cs = cases.CASES["c1_recursive_64"]
+    gold = np.load(os.path.join(cases.GOLDEN_DIR, "c1_recursive_64.npz"))
+    dec = gu.gpu_decoder("B")
+    K, R, T = cases.camera(cs["cam"], cs["hw"])
+    ren = pkg.SDFRenderer(dec, K, img_hw=cs["hw"], march_step=50, buffer_size=5, engine="simt")
+    Z, m, s = ren.render_depth(cases.synth.make_latent().cuda(), R.cuda(), T.cuda(), no_grad=True)
+    assert Z.dtype == torch.float32 and m.dtype == torch.bool and Z.shape == (64 * 64,)
+    zg = torch.from_numpy(gold["Zdepth_nograd"])
+    hit = zg < 1e10
+    assert bool(((Z.cpu() < 1e10) == hit).all())
+    assert gu.rel(Z.cpu()[hit], zg[hit]) < 1e-5
+
+
+def test_small_generic_network():
+    """Non-standard shape (width 64, 4 hidden layers, latent 16, latent_in=2) through the generic SIMT engine."""
+    dec_c = cases.synth.make_decoder("B", latent_size=16, width=64, depth=4, latent_in=2, seed=5)
+    import copy
+    dec_g = copy.deepcopy(dec_c).cuda()
+    cs = dict(decoder=None, hw=(24, 24), cam=("front", 1.6), march_step=30, buffer_size=3, kind="recursive")
+    out, g, _ = gu.run_gpu(cs, engine="simt", dec=dec_g)
+    ref, gref = gu.run_oracle(cs, dec=dec_c)
+    gu.compare(out, ref, g, gref)
+
+
+def test_row_band_sharding_equals_full():
+    """Rendering interleaved row bands (multi-GPU ray-tile sharding) reproduces the full image exactly."""
+    cs = cases.CASES["ragged_37x53"]
+    dec = gu.gpu_decoder("B")
+    K, R, T = cases.camera(cs["cam"], cs["hw"])
+    lat = cases.synth.make_latent().cuda()
+    full = pkg.SDFRenderer(dec, K, img_hw=cs["hw"], march_step=cs["march_step"], engine="simt").render(
+        lat, R.cuda(), T.cuda(), ray_marching_type="recursive", no_grad=True)
+    H = cs["hw"][0]
+    for r in range(3):
+        n_rows = len(range(r, H, 3))
+        part = pkg.SDFRenderer(dec, K, img_hw=cs["hw"], march_step=cs["march_step"], engine="simt",
+                               rows=(r, 3, n_rows)).render(lat, R.cuda(), T.cuda(), ray_marching_type="recursive",
+                                                           no_grad=True)
+        for a, b in zip(part, full):
+            assert torch.equal(a, b[r::3])
+
+
+def test_api_errors():
+    dec = gu.gpu_decoder("B")
+    K, R, T = cases.camera(("front", 1.6), (16, 16))
+    ren = pkg.SDFRenderer(dec, K, img_hw=(16, 16))
+    lat = cases.synth.make_latent().cuda()
+    with pytest.raises(NotImplementedError):
+        ren.render(lat, R.cuda(), T.cuda())            # default pyramid_recursive: not implemented yet, loudly
+    with pytest.raises(ValueError):
+        ren.render_depth(lat, R.cuda(), T.cuda(), ray_marching_type="bogus")
+    with pytest.raises(RuntimeError):
+        pkg.SDFRenderer(dec, K, img_hw=(16, 16), use_gpu=False)
+    with pytest.raises(ValueError):
+        pkg.SDFRenderer(cases.decoder("B"), K, img_hw=(16, 16))   # CPU decoder
+    K2 = K.copy()
+    K2[0, 2] += 4000.0
+    with pytest.raises(ValueError, match="No valid depth"):
+        pkg.SDFRenderer(dec, K2, img_hw=(16, 16)).render_depth(lat, R.cuda(), torch.tensor([0., 0., 50.]).cuda())
