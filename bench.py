@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""bench.py -- rays/s of the sphere-tracing hot path (BASELINE.json metric) on N GPUs of one node.
+
+  python bench.py --gpus N --steps K --warmup W          (N>1: launched under torch.distributed.run)
+  python bench.py --impl reference ...                   (CPU arm: oracle port of the reference, rank 0 only)
+
+A "step" is one full differentiable render of the workload -- SDFRenderer.render() (depth + normal + silhouette,
+50-step recursive march, buffer 5) with gradients enabled w.r.t. the 256-d latent, a scalar loss, and backward()
+-- on synthetic inputs (seeded geometric-init 8x512 DeepSDF decoder, seeded latent, fixed camera).  At N GPUs the
+image has round(512*sqrt(N))^2 pixels (same view, finer sampling), rows interleaved over ranks, so every GPU traces
+~512*512 rays (weak scaling); the per-rank bands and partial gradients are exchanged with ONE all-gather per step.
+
+`value`   : rays/s with inputs resident in HBM (CUDA events, max over ranks).
+`e2e`     : same metric through the public API with HOST buffers: H2D of latent/R/T from pinned memory and D2H of
+            all four output maps + the latent gradient inside the timed region.
+`roofline`: the decoder-row kernel (dominant) timed alone on a 262,144-row batch; achieved = rows/s * F
+            (F = 3,146,752 flop per folded row) against the measured dense bf16 peak of MEASURED_PEAKS.json.
+"""
+import argparse
+import importlib
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+HW_BASE = 512
+MARCH_STEP, BUFFER = 50, 5
+KIND = "recursive"
+CPU_SAMPLE_HW = 128
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops", 1590.0), d.get("bf16_tflops_sustained", 1400.0), d.get("hbm_gbs", 6650.0), "measured"
+    return 1590.0, 1400.0, 6650.0, "fallback"
+
+
+def loss_of(out):
+    depth, normal, mask, min_sdf = out
+    return depth[mask.bool()].sum() + min_sdf.sum()
+
+
+class ClockSampler(object):
+    """nvidia-smi sampling of SM clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.f, self.p = index, None, None
+
+    def __enter__(self):
+        try:
+            self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+        return self
+
+    def __exit__(self, *a):
+        if self.p is not None:
+            self.p.terminate()
+            try:
+                self.p.wait(timeout=5)
+            except Exception:
+                self.p.kill()
+
+    def summary(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.f is None:
+            return out
+        try:
+            self.f.flush()
+            rows = [l.split(",") for l in open(self.f.name).read().strip().splitlines() if l.count(",") >= 8]
+            sm = [float(r[1]) for r in rows]
+            if sm:
+                out["sm_mhz"] = statistics.median(sm)
+                out["sm_max_mhz"] = float(rows[0][2])
+                out["power_w_max"] = max(float(r[3]) for r in rows)
+                names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+                for i, n in enumerate(names):
+                    if any("Active" in r[5 + i] and "Not" not in r[5 + i] for r in rows):
+                        out["reasons"].append(n)
+                out["samples"] = len(rows)
+            os.unlink(self.f.name)
+        except Exception:
+            pass
+        return out
+
+
+def workload(n_gpus):
+    side = int(round(HW_BASE * math.sqrt(n_gpus)))
+    return side
+
+
+def run_reference(args, rank, world):
+    """CPU arm: the oracle port of the reference (oracle/sdf_oracle.py; the reference tree itself is Python and is
+    absent on the GPU box) on a bounded sample of the workload: a 128x128 render of the same view."""
+    if rank != 0:
+        return
+    from oracle.sdf_oracle import OracleSDFRenderer
+    synth = importlib.import_module("dist-renderer_b200.synth")
+    cores = pick_threads(synth)
+    dec = synth.make_decoder("B")
+    H = W = CPU_SAMPLE_HW
+    K = synth.intrinsic(H, W)
+    R, T = synth.front_camera()
+    ren = OracleSDFRenderer(dec, K, img_hw=(H, W), march_step=MARCH_STEP, buffer_size=BUFFER)
+    lat = synth.make_latent()
+
+    def step():
+        l = lat.clone().requires_grad_(True)
+        out = ren.render(l, R, T, ray_marching_type=KIND)
+        loss_of(out).backward()
+        return l.grad
+
+    for _ in range(min(args.warmup, 1)):
+        step()
+    t0 = time.time()
+    for _ in range(args.steps):
+        step()
+    dt = time.time() - t0
+    value = H * W * args.steps / dt
+    side = workload(args.gpus)
+    sample = "%dx%d render fwd+bwd of the same view (1/%d of the %dx%d workload's rays) per step" % (
+        H, W, (side * side) // (H * W), side, side)
+    line = {
+        "impl": "reference", "metric": "rays/sec (fwd+bwd)", "value": value, "unit": "rays/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_of(args.gpus, side),
+        "cpu_baseline": {"value": value, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def pick_threads(synth):
+    """Thread count that gives the oracle's decoder GEMMs the best throughput on this host (many-core boxes lose
+    badly to oversubscription at os.cpu_count() threads)."""
+    dec = synth.make_decoder("B")
+    x = torch.cat([synth.make_latent().expand(20000, -1), torch.rand(20000, 3) - 0.5], 1)
+    cores = os.cpu_count() or 1
+    best = (None, 1)
+    for n in sorted(set(min(cores, c) for c in (8, 16, 32, 64, 128))):
+        torch.set_num_threads(n)
+        with torch.no_grad():
+            dec.inference(x[:2000])
+            t0 = time.time()
+            dec.inference(x)
+            dt = time.time() - t0
+        if best[0] is None or dt < best[0]:
+            best = (dt, n)
+    torch.set_num_threads(best[1])
+    return best[1]
+
+
+def cpu_port_baseline(synth, lat_h, R_h, T_h, side, repeats=1):
+    """Oracle port of the reference on the host cores, bounded sample: a 128x128 render fwd+bwd of the same view."""
+    from oracle.sdf_oracle import OracleSDFRenderer
+    threads = pick_threads(synth)
+    dec_c = synth.make_decoder("B")
+    Hc = CPU_SAMPLE_HW
+    ora = OracleSDFRenderer(dec_c, synth.intrinsic(Hc, Hc), img_hw=(Hc, Hc), march_step=MARCH_STEP, buffer_size=BUFFER)
+    best = None
+    for _ in range(repeats):
+        l = lat_h.clone().requires_grad_(True)
+        t0 = time.time()
+        o = ora.render(l, R_h, T_h, ray_marching_type=KIND)
+        loss_of(o).backward()
+        dt = time.time() - t0
+        best = dt if best is None else min(best, dt)
+    return {"value": Hc * Hc / best, "unit": "rays/s", "cores": threads, "kind": "port",
+            "sample": "%dx%d render fwd+bwd of the same view (1/%d of the workload's rays), %d threads of %d host "
+                      "cores (best of a thread sweep)" % (Hc, Hc, side * side // (Hc * Hc), threads, os.cpu_count() or 1)}
+
+
+def config_of(n_gpus, side):
+    return {"workload": "%dx%d render(): depth+normal+silhouette, single shape (geometric-init 8x512 DeepSDF, 256-d "
+                        "latent), %d-step '%s' march, buffer %d, fwd + backward over the latent"
+                        % (side, side, MARCH_STEP, KIND, BUFFER),
+            "rays_per_gpu": side * side // n_gpus, "parallelism": "ray-tile (interleaved row bands) x%d" % n_gpus,
+            "l2": "flushed between timed iterations (256 MiB write)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--engine", default="auto")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    assert world == args.gpus or world == 1, "launch with torch.distributed.run --nproc-per-node N for --gpus N"
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    pkg = importlib.import_module("dist-renderer_b200")
+    synth = importlib.import_module("dist-renderer_b200.synth")
+    par = importlib.import_module("dist-renderer_b200.parallel")
+    abi = importlib.import_module("dist-renderer_b200._abi")
+    __import__("__graft_entry__").build()
+    lib = abi.lib()
+
+    side = workload(world)
+    dec = synth.make_decoder("B").to(dev)
+    K = synth.intrinsic(side, side)
+    R_h, T_h = synth.front_camera()
+    lat_h = synth.make_latent()
+    ren = par.ShardedSDFRenderer(dec, K, (side, side), rank=rank, world_size=world, march_step=MARCH_STEP,
+                                 buffer_size=BUFFER, engine=args.engine)
+    flush = torch.empty(64 * 1024 * 1024, device=dev, dtype=torch.float32)  # 256 MiB > 126 MB L2
+    lat_d, R_d, T_d = lat_h.to(dev), R_h.to(dev), T_h.to(dev)
+    n_lat = lat_h.numel()
+
+    def step_device(lat_src, R_src, T_src):
+        lat = lat_src.detach().requires_grad_(True)
+        out = ren.render(lat, R_src, T_src, ray_marching_type=KIND)
+        loss_of(out).backward()
+        full, extras = ren.gather(out, extra=lat.grad)
+        g = extras.sum(0) if extras is not None else lat.grad
+        return full, g
+
+    # ---- device-resident timing
+    for _ in range(args.warmup):
+        step_device(lat_d, R_d, T_d)
+        flush.fill_(1.0)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ren.local.reset_row_counter()
+    l0 = lib.dist_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clk:
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(args.steps):
+            full, g = step_device(lat_d, R_d, T_d)
+            flush.fill_(1.0)
+        e1.record()
+        torch.cuda.synchronize()
+    launches = lib.dist_launch_count() - l0
+    ms = e0.elapsed_time(e1)
+    rows_f, rows_g = int(ren.local.rows_evaluated.item()), int(ren.local.rows_grad.item())
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = side * side * args.steps / (ms * 1e-3)
+    clocks = clk.summary()
+
+    # ---- end to end through the public API with host buffers
+    pin = lambda x: x.clone().pin_memory()
+    lat_p, R_p, T_p = pin(lat_h), pin(R_h), pin(T_h)
+    outs_p = [torch.empty(side, side).pin_memory(), torch.empty(side, side, 3).pin_memory(),
+              torch.empty(side, side, dtype=torch.uint8).pin_memory(), torch.empty(side, side).pin_memory()]
+    g_p = torch.empty(n_lat).pin_memory()
+
+    def step_e2e():
+        full, g = step_device(lat_p.to(dev, non_blocking=True), R_p.to(dev, non_blocking=True),
+                              T_p.to(dev, non_blocking=True))
+        if rank == 0:
+            for dst, src in zip(outs_p, full):
+                dst.copy_(src, non_blocking=True)
+            g_p.copy_(g.reshape(-1), non_blocking=True)
+        torch.cuda.synchronize()
+
+    for _ in range(max(1, args.warmup // 2)):
+        step_e2e()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        step_e2e()
+        flush.fill_(1.0)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_e = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
+    t = torch.tensor([ms_e], device=dev)
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_e = float(t.item())
+    e2e_value = side * side * args.steps / (ms_e * 1e-3)
+    h2d = (lat_p.numel() + R_p.numel() + T_p.numel()) * 4
+    d2h = sum(o.numel() * o.element_size() for o in outs_p) + g_p.numel() * 4
+
+    # ---- roofline of the dominant kernel: decoder rows, timed alone (rank 0)
+    F = ren.local.flops_per_row()
+    roof = None
+    cpu_baseline = None
+    if rank == 0:
+        peak_burst, peak_sust, _, src = load_peaks()
+        n_rows = 262144
+        gen = torch.Generator().manual_seed(11)
+        pts = ((torch.rand(n_rows, 3, generator=gen) - 0.5) * 1.2).to(dev)
+        for _ in range(2):
+            pkg.decode_sdf(dec, lat_d, pts, clamp_dist=None, no_grad=True, engine=args.engine)
+        reps = 5
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            pkg.decode_sdf(dec, lat_d, pts, clamp_dist=None, no_grad=True, engine=args.engine)
+        e1.record()
+        torch.cuda.synchronize()
+        k_ms = e0.elapsed_time(e1) / reps
+        achieved = n_rows * F / (k_ms * 1e-3) / 1e12
+        in_step = (rows_f * F + rows_g * 2 * F) / (ms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "achieved": achieved, "peak": peak_burst, "unit": "TFLOP/s",
+                "frac": achieved / peak_burst, "traffic": None, "peak_source": src + " dense bf16 (burst)",
+                "kernel": "decoder-row tile kernel, %d rows/launch, %.3f ms/launch" % (n_rows, k_ms),
+                "flop_per_row": F, "in_step_tflops": in_step, "in_step_frac_of_sustained": in_step / peak_sust,
+                "rows_fwd_per_step": rows_f / args.steps, "rows_grad_per_step": rows_g / args.steps}
+        # ---- CPU baseline (oracle port) on a bounded sample, rank 0 at N=1 only
+        if world == 1 and not args.no_cpu_baseline:
+            cpu_baseline = cpu_port_baseline(synth, lat_h, R_h, T_h, side)
+    if rank == 0:
+        line = {
+            "metric": "rays/sec (fwd+bwd)", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32 (split-fp16 tensor-core operands, fp32 accumulate)"
+            if ren.local.plan.tc is not None else "f32", "data": "synthetic",
+            "config": config_of(world, side), "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e / args.steps},
+            "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu_baseline,
+            "engine": "tc" if ren.local.plan.tc is not None else "simt",
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

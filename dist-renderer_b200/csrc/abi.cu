@@ -1,6 +1,7 @@
 // extern "C" surface of libdist_b200.so (see include/dist_b200.h) + small shared helpers.
 #include <cuda_runtime.h>
 #include <stdarg.h>
+#include <atomic>
 #include <stdio.h>
 #include <string.h>
 #include "common.cuh"
@@ -8,6 +9,8 @@
 namespace dist {
 
 static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -77,6 +80,7 @@ extern "C" {
 
 int dist_abi_version(void) { return DIST_ABI_VERSION; }
 const char* dist_last_error(void) { return g_err; }
+long long dist_launch_count(void) { return g_launches.load(); }
 
 int dist_device_supports_tc(int device) {
   int major = 0;
@@ -92,15 +96,15 @@ int dist_fold_latent(const dist_net_t* net, const float* latent, float* out0, fl
     const int N = net->N[0], Np = round_up(N, 4);
     if (Lz > 0) {
       DIST_REQUIRE(latent && net->Wz0 && net->b0, "fold_latent: null latent buffers");
-      k_fold<<<(Np * 32 + 255) / 256, 256, 0, st>>>(net->Wz0, net->b0, latent, N, Lz, out0, Np);
+      k_fold<<<(Np * 32 + 255) / 256, 256, 0, st>>>(net->Wz0, net->b0, latent, N, Lz, out0, Np); count_launch();
     } else {
-      k_fold<<<(Np * 32 + 255) / 256, 256, 0, st>>>(net->b0, net->b0, net->b0, N, 0, out0, Np);
+      k_fold<<<(Np * 32 + 255) / 256, 256, 0, st>>>(net->b0, net->b0, net->b0, N, 0, out0, Np); count_launch();
     }
   }
   if (net->latent_in >= 0 && Lz > 0) {
     DIST_REQUIRE(outl && net->Wzl && net->bl, "fold_latent: null latent_in buffers");
     const int N = net->N[net->latent_in], Np = round_up(N, 4);
-    k_fold<<<(Np * 32 + 255) / 256, 256, 0, st>>>(net->Wzl, net->bl, latent, N, Lz, outl, Np);
+    k_fold<<<(Np * 32 + 255) / 256, 256, 0, st>>>(net->Wzl, net->bl, latent, N, Lz, outl, Np); count_launch();
   }
   DIST_CHECK_CUDA(cudaGetLastError());
   return DIST_OK;

@@ -8,6 +8,7 @@ namespace dist {
 
 void set_error(const char* fmt, ...);
 int num_sms();
+void count_launch();   // every kernel launch of the library is counted (dist_launch_count)
 
 #define DIST_CHECK_CUDA(expr)                                                                   \
   do {                                                                                          \

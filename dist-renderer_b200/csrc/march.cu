@@ -355,8 +355,8 @@ int render_depth_fwd(const dist_net_t* net, int engine, const dist_camera_t* cam
   const int S = mp->march_step;
   DIST_CHECK_CUDA(cudaMemsetAsync(ws->counts, 0, sizeof(int32_t) * (S + 2), st));
   const int tb = 256, gb = (P + tb - 1) / tb;
-  k_setup<<<gb, tb, 0, st>>>(cam, *mp, *ws, Zdepth, mask, min_sdf, P);
-  k_append_origin<<<1, 1, 0, st>>>(*ws, S + 1);
+  k_setup<<<gb, tb, 0, st>>>(cam, *mp, *ws, Zdepth, mask, min_sdf, P); count_launch();
+  k_append_origin<<<1, 1, 0, st>>>(*ws, S + 1); count_launch();
   DIST_CHECK_CUDA(cudaGetLastError());
   const int gu = min(gb, 4 * num_sms());
   for (int s = 0; s < S; ++s) {
@@ -366,9 +366,9 @@ int render_depth_fwd(const dist_net_t* net, int engine, const dist_camera_t* cam
     a.clamp_dist = 0.f; a.sdf = ws->sdf; a.rows_evaluated = rows_eval;
     rc = mlp_launch(net, nd, engine, 0, a, st);
     if (rc) return rc;
-    k_march_update<<<gu, tb, 0, st>>>(cam, *mp, *ws, s, P);
+    k_march_update<<<gu, tb, 0, st>>>(cam, *mp, *ws, s, P); count_launch();
   }
-  k_finalize<<<gb, tb, 0, st>>>(*mp, *ws, Zdepth, mask, min_sdf, P);
+  k_finalize<<<gb, tb, 0, st>>>(*mp, *ws, Zdepth, mask, min_sdf, P); count_launch();
   DIST_CHECK_CUDA(cudaGetLastError());
   return DIST_OK;
 }
@@ -386,13 +386,13 @@ int render_normal_fwd(const dist_net_t* net, int engine, const dist_camera_t* ca
   DIST_CHECK_CUDA(cudaMemsetAsync(s_count, 0, sizeof(int32_t), st));
   DIST_CHECK_CUDA(cudaMemsetAsync(Znormal, 0, sizeof(float) * 3 * (size_t)P, st));
   const int tb = 256, gb = (P + tb - 1) / tb;
-  k_normal_gen<<<gb, tb, 0, st>>>(cam, Zdepth, mask, s_idx, s_pts, s_count, P);
+  k_normal_gen<<<gb, tb, 0, st>>>(cam, Zdepth, mask, s_idx, s_pts, s_count, P); count_launch();
   MlpArgs a{};
   a.points = s_pts; a.n_host = P; a.n_dev = s_count; a.clamp_dist = clamp_dist; a.grad = s_grad;
   a.rows_evaluated = rows_eval;
   rc = mlp_launch(net, nd, engine, 1, a, st);
   if (rc) return rc;
-  k_normal_finish<<<min(gb, 4 * num_sms()), tb, 0, st>>>(cam, s_idx, s_grad, s_count, normalize, Znormal, P);
+  k_normal_finish<<<min(gb, 4 * num_sms()), tb, 0, st>>>(cam, s_idx, s_grad, s_count, normalize, Znormal, P); count_launch();
   DIST_CHECK_CUDA(cudaGetLastError());
   return DIST_OK;
 }
@@ -411,7 +411,7 @@ int render_depth_bwd(const dist_net_t* net, int engine, const dist_camera_t* cam
   const int P = cam.W * cam.n_rows;
   DIST_CHECK_CUDA(cudaMemsetAsync(s_count, 0, sizeof(int32_t), st));
   const int tb = 256, gb = (P + tb - 1) / tb;
-  k_bwd_gen<<<gb, tb, 0, st>>>(*mp, *ws, gZ, gM, s_row_pix, s_pts, s_coef, s_count, P);
+  k_bwd_gen<<<gb, tb, 0, st>>>(*mp, *ws, gZ, gM, s_row_pix, s_pts, s_coef, s_count, P); count_launch();
   MlpArgs a{};
   a.points = s_pts; a.n_host = (int64_t)P * mp->buffer_size; a.n_dev = s_count; a.clamp_dist = 0.f;
   a.grad = s_dpts; a.coef = s_coef; a.acc0 = acc0; a.accl = accl; a.rows_evaluated = rows_eval;
@@ -419,7 +419,7 @@ int render_depth_bwd(const dist_net_t* net, int engine, const dist_camera_t* cam
   if (rc) return rc;
   if (d_cam && d_ray) {
     k_bwd_scatter<<<min((int)(((int64_t)P * mp->buffer_size + tb - 1) / tb), 4 * num_sms()), tb, 0, st>>>(
-        cam, *ws, s_row_pix, s_dpts, s_count, d_cam, d_ray, P);
+        cam, *ws, s_row_pix, s_dpts, s_count, d_cam, d_ray, P); count_launch();
   }
   DIST_CHECK_CUDA(cudaGetLastError());
   return DIST_OK;

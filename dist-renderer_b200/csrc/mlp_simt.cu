@@ -304,9 +304,10 @@ int mlp_simt_launch(const NetDev& net, int mode, const MlpArgs& a, cudaStream_t 
   int64_t tiles = (a.n_host + TM - 1) / TM;
   int grid = (int)((tiles < (int64_t)num_sms()) ? tiles : (int64_t)num_sms());
   if (grid < 1) grid = 1;
-  if (mode == 0) mlp_simt_kernel<0><<<grid, NT, kSmemFwd, stream>>>(net, a);
-  else if (mode == 1) mlp_simt_kernel<1><<<grid, NT, kSmemGrad, stream>>>(net, a);
-  else mlp_simt_kernel<2><<<grid, NT, kSmemGrad, stream>>>(net, a);
+  if (mode == 0) { mlp_simt_kernel<0><<<grid, NT, kSmemFwd, stream>>>(net, a); }
+  else if (mode == 1) { mlp_simt_kernel<1><<<grid, NT, kSmemGrad, stream>>>(net, a); }
+  else { mlp_simt_kernel<2><<<grid, NT, kSmemGrad, stream>>>(net, a); }
+  count_launch();
   DIST_CHECK_CUDA(cudaGetLastError());
   return DIST_OK;
 }

@@ -109,7 +109,7 @@ class _RenderDepthFn(torch.autograd.Function):
             _abi.check(lib.dist_render_depth_bwd(net, ctx.engine, cam, ctx.mp, ws, _abi.ptr(gZ), _abi.ptr(gM),
                                                  _abi.ptr(acc0), _abi.ptr(accl), _abi.ptr(d_cam), _abi.ptr(d_ray),
                                                  _abi.ptr(s_row), _abi.ptr(s_pts), _abi.ptr(s_coef), None,
-                                                 _abi.ptr(s_dpts), _abi.ptr(s_cnt), _abi.ptr(ren.rows_evaluated), st))
+                                                 _abi.ptr(s_dpts), _abi.ptr(s_cnt), _abi.ptr(ren.rows_grad), st))
             if ctx.needs_input_grad[0] and latent is not None:
                 g_lat = plan.latent_grad(acc0, accl).reshape(latent.shape).to(latent.dtype)
             if want_cam:
@@ -169,7 +169,10 @@ class SDFRenderer(object):
             raise NotImplementedError("only 3x3 transform_matrix is supported (renderer.py:116 is dead code upstream)")
         self.transform_matrix = torch.from_numpy(transform_matrix).float().to(self.device)
         self.plan = plan_for(decoder)
+        # decoder-row counters for roofline accounting: forward rows cost F flop, gradient rows (normal / backward
+        # replay: forward + transposed chain) cost 2F
         self.rows_evaluated = torch.zeros(1, device=self.device, dtype=torch.int64)
+        self.rows_grad = torch.zeros(1, device=self.device, dtype=torch.int64)
         self._homo_calib = None
         self._calib_map = None
         self._scr = None
@@ -268,6 +271,11 @@ class SDFRenderer(object):
 
     def reset_row_counter(self):
         self.rows_evaluated.zero_()
+        self.rows_grad.zero_()
+
+    def flops_per_row(self):
+        """F = 2 * sum K_l N_l of the folded network (3,146,752 for the standard 8x512 spec)."""
+        return 2 * sum(k * n for k, n in zip(self.plan.K, self.plan.N))
 
     # ---- rendering --------------------------------------------------------------------------------------------
     def render_depth(self, latent, R, T, clamp_dist=0.1, sample_index_type='min_abs', profile=False, no_grad=False,
@@ -326,7 +334,7 @@ class SDFRenderer(object):
         _abi.check(lib.dist_render_normal_fwd(net, engine, cam, _abi.ptr(Zd), _abi.ptr(m8), float(clamp_dist),
                                               1 if normalize else 0, _abi.ptr(Znormal), _abi.ptr(scr["n_idx"]),
                                               _abi.ptr(scr["n_pts"]), _abi.ptr(scr["n_grad"]), _abi.ptr(scr["n_cnt"]),
-                                              _abi.ptr(self.rows_evaluated), st))
+                                              _abi.ptr(self.rows_grad), st))
         return Znormal
 
     def render(self, latent, R, T, clamp_dist=0.1, sample_index_type='min_abs', profile=False, no_grad=False,

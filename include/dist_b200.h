@@ -126,6 +126,8 @@ typedef struct dist_workspace {
 /* ---- library ---- */
 int dist_abi_version(void);
 const char* dist_last_error(void);
+/* number of CUDA kernels this library has launched in this process so far */
+long long dist_launch_count(void);
 /* 1 if the device has the tcgen05 path (compute capability 10.x) */
 int dist_device_supports_tc(int device);
 

@@ -74,7 +74,7 @@ def normal_error(n_a, n_b, mask, outlier_frac=0.001, outlier_thresh=1e-3):
     return r, int(bad.sum()), allowed
 
 
-def compare(out, ref, g=None, gref=None, tol=1e-4, gtol=2e-3, max_xor=2):
+def compare(out, ref, g=None, gref=None, tol=1e-4, gtol=2e-3, max_xor=2, threshold=5e-5):
     """Asserts the parity bar of BASELINE.md section 3 and returns the measured numbers."""
     m = out[2].bool() & ref[2].bool()
     xor = int((out[2] != ref[2]).sum())
@@ -85,8 +85,15 @@ def compare(out, ref, g=None, gref=None, tol=1e-4, gtol=2e-3, max_xor=2):
         assert res["depth"] < tol, res
         res["normal"], res["n_out"], allowed = normal_error(out[1], ref[1], m)
         assert res["normal"] < tol and res["n_out"] <= allowed, res
-    res["min_sdf"] = rel(out[3], ref[3])
-    assert res["min_sdf"] < tol, res
+    # min_sdf: a ray stops at the first sample with |sdf| < threshold (renderer.py:560), so where both renders
+    # converged the stored value is "some residual below the threshold" -- fp32 rounding decides whether the ray
+    # took one more step (e.g. 4.99e-5 stops, 5.01e-5 continues to -4.5e-5).  Those pixels are compared
+    # absolutely (|a-b| <= 2*threshold); everything else by rel-L2.
+    a, b = out[3].reshape(-1).double(), ref[3].reshape(-1).double()
+    conv = (a.abs() <= threshold) & (b.abs() <= threshold)
+    res["min_sdf"] = rel(a[~conv], b[~conv]) if bool((~conv).any()) else 0.0
+    res["min_sdf_converged_maxabs"] = float((a[conv] - b[conv]).abs().max()) if bool(conv.any()) else 0.0
+    assert res["min_sdf"] < tol and res["min_sdf_converged_maxabs"] <= 2 * threshold, res
     if g is not None:
         for name, a, b in zip(("g_latent", "g_R", "g_T"), g, gref):
             res[name] = rel(a, b)
