@@ -1,8 +1,464 @@
-// tcgen05 tensor-core engine (DIST_ENGINE_TC) -- placeholder until the UMMA tile kernel lands.
+// tcgen05 tensor-core engine for the folded DeepSDF decoder (DIST_ENGINE_TC), sm_100a only.
+//
+// A cluster of two CTAs (one SM pair) owns a tile of 128 decoder rows (64 per CTA) and carries it through the whole
+// network on-chip:
+//   * layer 0 (K = 3, xyz) and the last layer (N = 1, dot product + tanh) run on CUDA cores in the epilogue warps;
+//   * every hidden layer is a tcgen05.mma.cta_group::2.kind::f16 GEMM (M = 128 over the pair, N = 256 per instruction,
+//     K = 16) with split-fp16 operands: D += A_hi*W_hi + A_lo*W_hi + A_hi*W_lo, fp32 accumulation in TMEM
+//     (see tc.py for the precision argument);
+//   * A (activations, 64 rows x K x {hi,lo} fp16 = 128 KB) is resident in shared memory in the UMMA no-swizzle
+//     K-major "panel" layout and is rewritten in place by the epilogue of each layer (TMEM -> registers -> bias,
+//     ReLU, split -> smem); it never touches HBM;
+//   * W streams L2 -> smem through a 6-stage ring of 16 KB TMA box copies per CTA (each CTA holds half of the
+//     256 N-rows of a stage; `.cta_group::2` copies signal the leader CTA's mbarrier), released by tcgen05.commit;
+//   * accumulators ping-pong between two 256-column TMEM buffers so the epilogue of layer l overlaps the MMAs of
+//     layer l+1 chunk by chunk (per-64-feature `a_full` barriers).
+// Warp roles per CTA (384 threads): warp 0 TMA producer, warp 1 MMA issuer (leader CTA), warp 2 TMEM allocator,
+// warps 4-11 epilogue (TMEM lane quarter = warp % 4, column half = (warp-4)/4).
+//
+// Replaces: Decoder.inference / decode_sdf (core/graph/deep_sdf_decoder.py:80-111, core/utils/decoder_utils.py:53-74)
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <string.h>
 #include "common.cuh"
+
 namespace dist {
-int mlp_tc_launch(const dist_net_t*, const NetDev&, int, const MlpArgs&, cudaStream_t) {
-  set_error("tensor-core engine not built in this library");
-  return DIST_E_UNSUPPORTED;
+namespace {
+
+constexpr int NST = 6;                 // weight ring stages
+constexpr int STAGE_BYTES = 16384;     // per CTA: [hi 8 KB][lo 8 KB]
+constexpr int OFF_AHI = 0, OFF_ALO = 65536, OFF_W = 131072;
+constexpr int OFF_BAR = OFF_W + NST * STAGE_BYTES;   // 229376
+constexpr int OFF_PART = OFF_BAR + 512;              // per-row partial sums of the last layer [64][4]
+constexpr int SMEM_BYTES = OFF_PART + 1024;          // 230912
+constexpr int NTHREADS = 384;
+constexpr int MAX_TC_LAYERS = 2 * DIST_MAX_LAYERS;
+
+struct LayerTC {
+  int kc32;          // number of 32-wide K chunks (K padded to a multiple of 64)
+  int nh;            // number of 256-wide N halves
+  int stage_base;    // first stage of this layer in the blob
+  int N;             // logical outputs of this layer
+  int app_xyz;       // 1: append xyz at columns N..N+2 of the produced activation (next layer is latent_in)
+  float inv_scale;   // 1 / (sA * sW)
+  const float* bias;
+};
+
+struct TcParams {
+  int n_mma;                       // tensor-core layers (net layers 1 .. n-2)
+  LayerTC L[DIST_MAX_LAYERS];
+  const float* w0;                 // Wt[0]: [8][N0p4], rows 0..2 = weights of x,y,z
+  const float* bias0;
+  int N0, N0p4;
+  const float* wlast;              // W[last] row 0, [K_last]
+  const float* blast;
+  int K_last;
+  int use_tanh;
+  float sA;
+  int first_append;                // layer 0's output gets xyz appended (latent_in == 1)
+};
+
+// --------------------------------------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
 }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n.reg .pred p;\nWAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+// wait with cluster-scope acquire: for barriers the peer CTA arrives on remotely
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n.reg .pred p;\nWAIT_%=:\n"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+// arrive (count 1) on the barrier at the same smem offset in CTA `target_rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_local, uint32_t target_rank) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(bar_local), "r"(target_rank));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(lbo >> 4) << 16;
+  d |= (uint64_t)(sbo >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+__device__ __forceinline__ void mma_f16_2cta(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void commit_mc(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,"
+      "%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Writes 8 consecutive features (one K-group panel row) of this thread's row: x[] already multiplied by sA.
+__device__ __forceinline__ void store_group(uint8_t* smem, int feat0, int row, const float* x) {
+  __half2 h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    h[i] = __floats2half2_rn(x[2 * i], x[2 * i + 1]);
+    const float2 hf = __half22float2(h[i]);
+    l[i] = __floats2half2_rn(x[2 * i] - hf.x, x[2 * i + 1] - hf.y);
+  }
+  const int off = (feat0 >> 3) * 1024 + row * 16;
+  *reinterpret_cast<uint4*>(smem + OFF_AHI + off) = *reinterpret_cast<uint4*>(h);
+  *reinterpret_cast<uint4*>(smem + OFF_ALO + off) = *reinterpret_cast<uint4*>(l);
+}
+
+// --------------------------------------------------------------------------------------------- kernel
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
+mlp_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P, const float* __restrict__ points,
+                  int64_t n_host, const int32_t* __restrict__ n_dev, float clamp_dist, float* __restrict__ sdf_out,
+                  int64_t* rows_evaluated) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int64_t n = n_dev ? (int64_t)*n_dev : n_host;
+  if (n <= 0) return;
+  const uint32_t rank = cluster_ctarank();
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  const int64_t n_tiles = (n + 127) / 128;
+  if (blockIdx.x == 0 && tid == 0 && rows_evaluated)
+    atomicAdd(reinterpret_cast<unsigned long long*>(rows_evaluated), (unsigned long long)n);
+
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar0 = sbase + OFF_BAR;
+  auto W_FULL = [&](int s) { return bar0 + 8 * s; };
+  auto W_EMPTY = [&](int s) { return bar0 + 8 * (NST + s); };
+  auto A_FULL = [&](int c) { return bar0 + 8 * (2 * NST + c); };
+  auto D_FULL = [&](int b) { return bar0 + 8 * (2 * NST + 8 + b); };
+  const uint32_t FIN = bar0 + 8 * (2 * NST + 10);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 8 * (2 * NST + 11));
+
+  if (tid == 0) {
+    for (int s = 0; s < NST; ++s) { mbar_init(W_FULL(s), 1); mbar_init(W_EMPTY(s), 1); }
+    for (int c = 0; c < 8; ++c) mbar_init(A_FULL(c), 4);   // 2 warps x 2 CTAs produce each 64-feature chunk
+    mbar_init(D_FULL(0), 1); mbar_init(D_FULL(1), 1);
+    mbar_init(FIN, 16);                                     // 8 epilogue warps x 2 CTAs
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // =============================================================== TMA producer (both CTAs)
+    if (lane == 0) {
+      uint32_t it = 0;
+      const uint32_t bar_leader_mask = 0xFEFFFFFFu;
+      for (int64_t t = cluster_id; t < n_tiles; t += n_clusters) {
+        for (int m = 0; m < P.n_mma; ++m) {
+          const LayerTC& L = P.L[m];
+          const int nstage = L.kc32 * L.nh;
+          for (int s = 0; s < nstage; ++s, ++it) {
+            const int slot = it % NST;
+            const uint32_t ph = (it / NST) & 1;
+            mbar_wait(W_EMPTY(slot), ph ^ 1);
+            if (rank == 0) mbar_expect_tx(W_FULL(slot), 2 * STAGE_BYTES);
+            const int row = ((L.stage_base + s) * 2 + (int)rank) * (STAGE_BYTES / 128);
+            asm volatile(
+                "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
+                    "r"(sbase + OFF_W + slot * STAGE_BYTES),
+                "l"(&tmap), "r"(W_FULL(slot) & bar_leader_mask), "r"(0), "r"(row)
+                : "memory");
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // =============================================================== MMA issuer (leader CTA, one thread)
+    if (rank == 0 && lane == 0) {
+      const uint32_t idesc = (1u << 4) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
+      uint32_t it = 0, G = 0, a_phase = 0, fin_phase = 0;
+      uint32_t d_first = 1;
+      for (int64_t t = cluster_id; t < n_tiles; t += n_clusters) {
+        for (int m = 0; m < P.n_mma; ++m, ++G) {
+          const LayerTC& L = P.L[m];
+          const uint32_t buf = G & 1;
+          // the final-layer accumulator of the previous tile lives in this buffer until its epilogue drained it
+          if (m == 1 && !d_first) { mbar_wait_cluster(FIN, fin_phase); fin_phase ^= 1; tc_fence_after(); }
+          for (int kc = 0; kc < L.kc32; ++kc) {
+            if ((kc & 1) == 0) {
+              const int c = kc >> 1;
+              mbar_wait_cluster(A_FULL(c), (a_phase >> c) & 1);
+              a_phase ^= (1u << c);
+              tc_fence_after();
+            }
+            for (int h = 0; h < L.nh; ++h, ++it) {
+              const int slot = it % NST;
+              mbar_wait(W_FULL(slot), (it / NST) & 1);
+              tc_fence_after();
+              const uint32_t d_addr = tmem + buf * 256 + h * 128;
+              const uint32_t wb = sbase + OFF_W + slot * STAGE_BYTES;
+#pragma unroll
+              for (int ks = 0; ks < 2; ++ks) {
+                const uint32_t a_off = (uint32_t)(kc * 4 + ks * 2) * 1024;
+                const uint64_t a_hi = make_desc(sbase + OFF_AHI + a_off, 1024, 128);
+                const uint64_t a_lo = make_desc(sbase + OFF_ALO + a_off, 1024, 128);
+                const uint64_t b_hi = make_desc(wb + ks * 2 * 2048, 2048, 128);
+                const uint64_t b_lo = make_desc(wb + 8192 + ks * 2 * 2048, 2048, 128);
+                mma_f16_2cta(d_addr, a_hi, b_hi, idesc, (kc | ks) ? 1u : 0u);
+                mma_f16_2cta(d_addr, a_lo, b_hi, idesc, 1u);
+                mma_f16_2cta(d_addr, a_hi, b_lo, idesc, 1u);
+              }
+              commit_mc(W_EMPTY(slot));
+            }
+          }
+          commit_mc(D_FULL(buf));
+        }
+        d_first = 0;
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // =============================================================== epilogue warps
+    const int ew = warp - 4;
+    const int qq = warp & 3;             // TMEM lane quarter accessible to this warp
+    const int q = qq >> 1;               // which 128-feature half of an N-half this lane quarter holds
+    const int ch = ew >> 2;              // which 64-column half of those 128 this warp handles
+    const int row = 32 * (qq & 1) + lane;
+    const uint32_t lane_base = (uint32_t)(32 * qq) << 16;
+    const float sA = P.sA;
+    uint32_t G = 0, d_phase = 0;
+    float px = 0.f, py = 0.f, pz = 0.f;
+
+    auto load_point = [&](int64_t t) {
+      const int64_t gr = t * 128 + rank * 64 + row;
+      if (gr < n) { px = points[gr * 3]; py = points[gr * 3 + 1]; pz = points[gr * 3 + 2]; }
+      else { px = py = pz = 0.f; }
+    };
+    auto signal_chunk = [&](int c) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(A_FULL(c), 0);
+    };
+    // layer 0 on CUDA cores: A <- split(sA * relu(b0' + W0 xyz)), features of this thread's chunks
+    auto layer0 = [&]() {
+      const int kchunks = P.L[0].kc32 >> 1;                    // 64-feature chunks the first MMA layer consumes
+      const int nh0 = (P.N0 + 255) >> 8;
+      for (int h = 0; h < nh0; ++h) {
+        const int c = 4 * h + 2 * q + ch;
+        if (c >= kchunks) continue;
+        const int f0 = 64 * c;
+#pragma unroll 1
+        for (int g = 0; g < 8; ++g) {
+          float x[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int f = f0 + 8 * g + e;
+            float v = 0.f;
+            if (f < P.N0) {
+              v = fmaf(__ldg(P.w0 + 2 * P.N0p4 + f), pz, fmaf(__ldg(P.w0 + P.N0p4 + f), py, __ldg(P.w0 + f) * px)) + __ldg(P.bias0 + f);
+              v = fmaxf(v, 0.f);
+            } else if (P.first_append && f < P.N0 + 3) {
+              v = (f == P.N0) ? px : ((f == P.N0 + 1) ? py : pz);
+            }
+            x[e] = v * sA;
+          }
+          store_group(smem, f0 + 8 * g, row, x);
+        }
+        signal_chunk(c);
+      }
+    };
+
+    int64_t t = cluster_id;
+    if (t < n_tiles) { load_point(t); layer0(); }
+    for (; t < n_tiles; t += n_clusters) {
+      const int64_t gr = t * 128 + rank * 64 + row;
+      float dot = 0.f;
+      for (int m = 0; m < P.n_mma; ++m, ++G) {
+        const LayerTC& L = P.L[m];
+        const uint32_t buf = G & 1;
+        const bool is_last = (m == P.n_mma - 1);
+        mbar_wait(D_FULL(buf), (d_phase >> buf) & 1);
+        d_phase ^= (1u << buf);
+        tc_fence_after();
+        if (is_last) {
+          // all MMAs of this tile are complete: A is free -> start the next tile's layer 0 before draining D
+          if (t + n_clusters < n_tiles) { load_point(t + n_clusters); layer0(); }
+        }
+        const int kchunks_next = is_last ? 0 : (P.L[m + 1].kc32 >> 1);
+        const float cscale = L.inv_scale;
+        for (int h = 0; h < L.nh; ++h) {
+          const int c = 4 * h + 2 * q + ch;
+          const int f0 = 256 * h + 128 * q + 64 * ch;
+          if (!is_last && c >= kchunks_next) continue;
+          if (is_last && f0 >= L.N) continue;
+#pragma unroll 1
+          for (int sub = 0; sub < 2; ++sub) {
+            float v[32];
+            tmem_ld32(tmem + lane_base + buf * 256 + h * 128 + 64 * ch + 32 * sub, v);
+            const int fb = f0 + 32 * sub;
+            if (is_last) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const int f = fb + j;
+                if (f < L.N) {
+                  const float a = fmaxf(fmaf(v[j], cscale, __ldg(L.bias + f)), 0.f);
+                  dot = fmaf(a, __ldg(P.wlast + f), dot);
+                }
+              }
+            } else {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                float x[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  const int f = fb + 8 * g + e;
+                  float a = 0.f;
+                  if (f < L.N) a = fmaxf(fmaf(v[8 * g + e], cscale, __ldg(L.bias + f)), 0.f);
+                  else if (L.app_xyz && f < L.N + 3) a = (f == L.N) ? px : ((f == L.N + 1) ? py : pz);
+                  x[e] = a * sA;
+                }
+                store_group(smem, fb + 8 * g, row, x);
+              }
+            }
+          }
+          if (!is_last) signal_chunk(c);
+        }
+        if (is_last) {
+          // the accumulator of the final layer is drained: release it for the second MMA layer of the next tile
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(FIN, 0);
+          // combine the 4 partial dot products of each row (q x ch) and finish: bias, tanh (deep_sdf_decoder.py:109-110)
+          float* part = reinterpret_cast<float*>(smem + OFF_PART);
+          part[row * 4 + 2 * q + ch] = dot;
+          epi_bar_sync();
+          if (q == 0 && ch == 0) {
+            float s = (part[row * 4] + part[row * 4 + 1]) + (part[row * 4 + 2] + part[row * 4 + 3]) + __ldg(P.blast);
+            float o = tanhf(s);
+            if (P.use_tanh) o = tanhf(o);
+            if (clamp_dist > 0.f) o = fminf(fmaxf(o, -clamp_dist), clamp_dist);
+            if (gr < n) sdf_out[gr] = o;
+          }
+          epi_bar_sync();
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+}
+
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                             const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeFn get_encode() {
+  static EncodeFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    cudaDriverEntryPointQueryResult q;
+    void* p = nullptr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess) fn = (EncodeFn)p;
+  }
+  return fn;
+}
+
+}  // namespace
+
+int mlp_tc_launch(const dist_net_t* net, const NetDev& nd, int mode, const MlpArgs& a, cudaStream_t stream) {
+  if (mode != 0) return mlp_simt_launch(nd, mode, a, stream);  // gradient chains: fp32 engine (for now)
+  DIST_REQUIRE(net->tc_blob && net->tc_scale, "tensor-core engine: operands not prepared (tc.prepare)");
+  const int nl = nd.n_layers;
+  DIST_REQUIRE(nl >= 4 && nl <= 10, "tensor-core engine: %d layers unsupported", nl);
+  if (a.n_host <= 0 && !a.n_dev) return DIST_OK;
+  EncodeFn encode = get_encode();
+  if (!encode) { set_error("cuTensorMapEncodeTiled not available"); return DIST_E_UNSUPPORTED; }
+
+  TcParams P;
+  memset(&P, 0, sizeof(P));
+  P.n_mma = nl - 2;
+  int stage = 0;
+  for (int m = 0; m < P.n_mma; ++m) {
+    const int l = m + 1;
+    LayerTC& L = P.L[m];
+    L.kc32 = round_up(nd.K[l], 64) / 32;
+    L.nh = (nd.N[l] + 255) / 256;
+    L.stage_base = stage;
+    stage += L.kc32 * L.nh;
+    L.N = nd.N[l];
+    L.app_xyz = (l + 1 == nd.latent_in) ? 1 : 0;
+    L.inv_scale = net->tc_scale[m];
+    L.bias = nd.bias[l];
+    DIST_REQUIRE(nd.N[l] + 3 * L.app_xyz <= 256 * L.nh && nd.N[l] <= 512, "tensor-core engine: layer %d width unsupported", l);
+  }
+  P.w0 = nd.Wt[0]; P.bias0 = nd.bias[0]; P.N0 = nd.N[0]; P.N0p4 = round_up(nd.N[0], 4);
+  P.wlast = nd.W[nl - 1]; P.blast = nd.bias[nl - 1]; P.K_last = nd.K[nl - 1];
+  P.use_tanh = nd.use_tanh; P.sA = 32.0f;
+  P.first_append = (nd.latent_in == 1) ? 1 : 0;
+
+  // tensor map over the blob: rows of 128 B; one box = one 16 KB stage of one CTA
+  CUtensorMap tmap;
+  const cuuint64_t rows = (cuuint64_t)(net->tc_blob_bytes / 128);
+  const cuuint64_t gdim[2] = {64, rows};
+  const cuuint64_t gstr[1] = {128};
+  const cuuint32_t box[2] = {64, STAGE_BYTES / 128};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(net->tc_blob), gdim, gstr, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)cr); return DIST_E_CUDA; }
+
+  static bool attr_done = false;
+  if (!attr_done) {
+    DIST_CHECK_CUDA(cudaFuncSetAttribute(mlp_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_done = true;
+  }
+  const int64_t tiles = (a.n_host + 127) / 128;
+  int clusters = num_sms() / 2;
+  if (tiles < clusters) clusters = (int)tiles;
+  if (clusters < 1) clusters = 1;
+  mlp_tc_fwd_kernel<<<clusters * 2, NTHREADS, SMEM_BYTES, stream>>>(tmap, P, a.points, a.n_host, a.n_dev, a.clamp_dist, a.sdf,
+                                                                   a.rows_evaluated); count_launch();
+  DIST_CHECK_CUDA(cudaGetLastError());
+  return DIST_OK;
+}
+
 }  // namespace dist

@@ -147,7 +147,9 @@ class DecoderPlan(object):
         if self.latent_in >= 0:
             net.Wzl, net.bl = self.Wzl.data_ptr(), self.bl.data_ptr()
         if self.tc is not None:
-            net.tc_blob, net.tc_scale = self.tc["blob"].data_ptr(), self.tc["scale"].data_ptr()
+            import ctypes
+            net.tc_blob = self.tc["blob"].data_ptr()
+            net.tc_scale = ctypes.addressof(self.tc["inv_scale"])
             net.tc_blob_bytes = self.tc["blob"].numel() * self.tc["blob"].element_size()
         return net
 

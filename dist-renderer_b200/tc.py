@@ -1,10 +1,157 @@
-"""Tensor-core engine operand preparation (split-fp16 weight tiles for csrc/mlp_tc.cu)."""
+"""Tensor-core engine operand preparation (split-fp16 weight tiles for csrc/mlp_tc.cu).
+
+Precision scheme (single-pass TF32/BF16 breaks the 5e-5 convergence test): every fp32 operand x is
+represented as hi + lo with hi = fp16(s*x), lo = fp16(s*x - hi) for a power-of-two scale s, and each logical GEMM
+is issued as three fp16 tensor-core passes  A_hi*W_hi + A_lo*W_hi + A_hi*W_lo  with fp32 accumulation in TMEM
+(the dropped lo*lo term is 2^-22 relative).  fp16 (11-bit significand) x 2 carries 22 bits -- the precision of the
+"TF32x2" row of SURVEY Table P -- at the fp16/bf16 MMA rate (2x the TF32 rate) and half the operand bytes.
+
+Blob layout (must match csrc/mlp_tc.cu): for each tensor-core layer, for each 32-wide K chunk kc, for each
+256-wide N half h, for each CTA r of the pair: a 16 KB stage = [hi 8 KB][lo 8 KB], each
+[4 K-groups][128 n-rows][8 k] fp16 holding  W[n = 256 h + 128 r + row][k = 32 kc + 8 g + e] * sW  -- the no-swizzle
+K-major "panel" image the UMMA shared-memory descriptor reads (LBO = 2048 B between K-groups, SBO = 128 B between
+8-row groups), so one TMA box copy lands a stage without any reshuffling.
+The transposed chain (input-gradient / backward) uses the same layout built from W^T.
+"""
+import math
+
+import torch
+
+from . import _abi
+
+S_ACT = 32.0        # activation scale (power of two): post-ReLU activations up to ~2000 stay finite in fp16
+S_GRAD = 256.0      # scale of the backward-chain operand (d sdf / d pre-activation, unit seed)
 
 
 def supported(plan):
     """True when the tcgen05 engine covers this decoder shape on this device."""
-    return False
+    if not torch.cuda.is_available():
+        return False
+    if _abi.lib().dist_device_supports_tc(plan.device.index if plan.device.index is not None else 0) != 1:
+        return False
+    n = plan.n_layers
+    if n < 4 or n > 10:
+        return False
+    if plan.K[0] != 3:
+        return False
+    for l in range(n - 1):
+        if plan.N[l] > 512:
+            return False
+        app = 3 if (l + 1 == plan.latent_in) else 0
+        if plan.N[l] + app > 256 * ((plan.N[l] + 255) // 256):
+            return False
+    return True
+
+
+def _pow2_scale(w, target_log2=14):
+    m = float(w.abs().max())
+    if m == 0.0 or not math.isfinite(m):
+        return 1.0
+    return 2.0 ** (target_log2 - 1 - math.floor(math.log2(m)))
+
+
+def _split(x):
+    hi = x.half()
+    lo = (x - hi.float()).half()
+    return hi, lo
+
+
+def _tiles(w, scale, c_trunc):
+    """w: [N, K] fp32 (logical B operand: N output rows, K reduction).  Returns the stage blob for this layer as a
+    flat fp16 tensor plus (k chunks of 32, n halves).
+
+    Truncation pre-compensation: the tensor core adds each K=16 block into the fp32 accumulator with truncation
+    (round toward zero), i.e. every one of the 3*J accumulation steps of a layer loses on average c*S_i of the
+    running sum S_i.  The expected loss  -c * sum_i S_i = -c * sum_j 3(J-j) p_j  is a linear functional of the block
+    products p_j, so scaling the weights of K-block j by (1 + 3c(J-j)) cancels it to first order (c is measured on
+    the device by calibrate()).  What remains is zero-mean rounding noise of the size of an fp32 sequential sum's."""
+    N, K = w.shape
+    Kp, NH = ((K + 63) // 64) * 64, (N + 255) // 256
+    wp = torch.zeros(NH * 256, Kp, device=w.device, dtype=torch.float64)
+    J = Kp // 16
+    comp = 1.0 + 3.0 * c_trunc * (J - torch.arange(Kp, device=w.device, dtype=torch.float64) // 16)
+    wp[:N, :K] = w.double() * scale
+    wp = (wp * comp[None, :]).float()
+    hi, lo = _split(wp)
+    kc = Kp // 32
+
+    def panels(t):  # [NH*256, Kp] -> [kc, NH, 2(r), 4(g), 128(row), 8(e)]
+        return t.reshape(NH, 2, 128, kc, 4, 8).permute(3, 0, 1, 4, 2, 5)
+    both = torch.stack([panels(hi), panels(lo)], 3)          # [kc, NH, r, hi/lo, g, row, e]
+    return both.contiguous().reshape(-1), kc, NH
+
+
+_C_TRUNC = None     # measured per-accumulation truncation loss of the tcgen05 fp32 accumulator (see _tiles)
+
+
+def calibrate(plan, n_points=8192):
+    """Measures the truncation constant c on this device: the final-sdf deviation of the tensor-core engine from the
+    exact-fp32 SIMT engine is linear in the compensation constant, so two probes (c = 0 and c = c1) give its root."""
+    global _C_TRUNC
+    if _C_TRUNC is not None:
+        return _C_TRUNC
+    lib = _abi.lib()
+    st = torch.cuda.current_stream().cuda_stream
+    g = torch.Generator().manual_seed(1234)
+    pts = ((torch.rand(n_points, 3, generator=g) - 0.5) * 1.2).to(plan.device)
+    lat = torch.zeros(plan.latent_size, device=plan.device) if plan.latent_size > 0 else None
+    b0, bl, _ = plan.fold(lat, st)
+    ref = torch.empty(n_points, device=plan.device)
+    saved = plan.tc
+    plan.tc = None
+    _abi.check(lib.dist_decoder_forward(plan.c_net(b0, bl), _abi.ENGINE_SIMT, _abi.ptr(pts), n_points, None, 0.0,
+                                        _abi.ptr(ref), st))
+
+    def probe(c):
+        plan.tc = _build(plan, c)
+        out = torch.empty(n_points, device=plan.device)
+        _abi.check(lib.dist_decoder_forward(plan.c_net(b0, bl), _abi.ENGINE_TC, _abi.ptr(pts), n_points, None, 0.0,
+                                            _abi.ptr(out), st))
+        return float((out.double() - ref.double()).mean())
+    c1 = 4.0e-8
+    e0, e1 = probe(0.0), probe(c1)
+    plan.tc = saved
+    c = c1 * e0 / (e0 - e1) if abs(e0 - e1) > 1e-12 else 0.0
+    if not (0.0 <= c <= 4.0e-7):      # outside anything physical: do not compensate
+        c = 0.0
+    _C_TRUNC = c
+    return c
 
 
 def prepare(plan):
-    raise NotImplementedError("tensor-core engine not available yet")
+    """Builds (once per weight version) the device blobs for the forward and the transposed chain."""
+    if plan.tc is not None:
+        return plan.tc
+    if not supported(plan):
+        raise NotImplementedError("the tensor-core engine does not cover this decoder shape / device")
+    c = calibrate(plan)
+    plan.tc = _build(plan, c)
+    return plan.tc
+
+
+def _build(plan, c_trunc):
+    n = plan.n_layers
+    blobs, meta = [], []
+    stage = 0
+    # forward: tensor-core layers are net layers 1 .. n-2
+    for l in range(1, n - 1):
+        w = plan.W[l][: plan.N[l], : plan.K[l]]
+        s = _pow2_scale(w)
+        b, kc, nh = _tiles(w, s, c_trunc)
+        blobs.append(b)
+        meta.append([kc, nh, stage, 1.0 / (S_ACT * s)])
+        stage += kc * nh
+    # transposed chain: gradient w.r.t. the input of net layer l (l = n-2 .. 1): B operand = W_l^T  ([K_l, N_l])
+    for l in range(n - 2, 0, -1):
+        w = plan.W[l][: plan.N[l], : plan.K[l]].t().contiguous()
+        s = _pow2_scale(w)
+        b, kc, nh = _tiles(w, s, c_trunc)
+        blobs.append(b)
+        meta.append([kc, nh, stage, 1.0 / (S_GRAD * s)])
+        stage += kc * nh
+    blob = torch.cat(blobs).contiguous()
+    assert blob.numel() * 2 == stage * 2 * 16384
+    # meta as float tensor rows: kc, nh, stage_base, inv_scale  (read on the host side of the C ABI only)
+    import ctypes
+    inv = (ctypes.c_float * len(meta))(*[m[3] for m in meta])   # HOST array read by the launch code of the C ABI
+    return {"blob": blob, "inv_scale": inv, "meta": meta, "n_fwd": n - 2, "stages": stage, "c_trunc": c_trunc}

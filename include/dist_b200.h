@@ -69,7 +69,7 @@ typedef struct dist_net {
   const float* bl;            /* unfolded bias of the latent_in layer */
   /* tensor-core engine operands (NULL when only the SIMT engine is prepared) */
   const void* tc_blob;        /* split-fp16 weight tiles, see csrc/mlp_tc.cu */
-  const float* tc_scale;      /* per-layer power-of-two operand scales */
+  const float* tc_scale;      /* HOST array: 1/(sA*sW) per tensor-core layer (forward layers, then the transposed chain) */
   int64_t tc_blob_bytes;
 } dist_net_t;
 

