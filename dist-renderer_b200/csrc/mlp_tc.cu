@@ -30,24 +30,29 @@ constexpr int NST = 6;                 // weight ring stages
 constexpr int STAGE_BYTES = 16384;     // per CTA: [hi 8 KB][lo 8 KB]
 constexpr int OFF_AHI = 0, OFF_ALO = 65536, OFF_W = 131072;
 constexpr int OFF_BAR = OFF_W + NST * STAGE_BYTES;   // 229376
-constexpr int OFF_PART = OFF_BAR + 512;              // per-row partial sums of the last layer [64][4]
-constexpr int SMEM_BYTES = OFF_PART + 1024;          // 230912
+constexpr int OFF_PART = OFF_BAR + 256;              // per-row partial sums [64][4] (4 threads share a row)
+constexpr int OFF_ROWD = OFF_PART + 1024;            // per-row scalar [64]
+constexpr int SMEM_BYTES = OFF_ROWD + 256;           // 230912
 constexpr int NTHREADS = 384;
-constexpr int MAX_TC_LAYERS = 2 * DIST_MAX_LAYERS;
+constexpr int MAX_PROG = 2 * 10;                     // forward + transposed chain, at most 10 tensor-core layers each
 
 struct LayerTC {
   int kc32;          // number of 32-wide K chunks (K padded to a multiple of 64)
   int nh;            // number of 256-wide N halves
   int stage_base;    // first stage of this layer in the blob
-  int N;             // logical outputs of this layer
-  int app_xyz;       // 1: append xyz at columns N..N+2 of the produced activation (next layer is latent_in)
-  float inv_scale;   // 1 / (sA * sW)
+  int N;             // forward: logical outputs (hidden width); transposed chain: hidden width of the PREVIOUS net layer
+  int app_xyz;       // forward: append xyz at columns N..N+2 of the produced activation (next layer is latent_in)
+                     // transposed chain: columns N..N+2 of the result are d/dxyz (this net layer is latent_in)
+  float inv_scale;   // 1 / (operand scale * weight scale)
   const float* bias;
 };
 
 struct TcParams {
-  int n_mma;                       // tensor-core layers (net layers 1 .. n-2)
-  LayerTC L[DIST_MAX_LAYERS];
+  int n_mma;                       // tensor-core layers of the forward pass (net layers 1 .. n-2)
+  int n_prog;                      // layers per tile: n_mma (forward only) or 2 n_mma (forward + transposed chain)
+  int acc_l_prog;                  // program layer whose produced delta is accumulated into accl (-1: none)
+  int accl_N;                      // width of the latent_in layer
+  LayerTC L[MAX_PROG];
   const float* w0;                 // Wt[0]: [8][N0p4], rows 0..2 = weights of x,y,z
   const float* bias0;
   int N0, N0p4;
@@ -55,8 +60,14 @@ struct TcParams {
   const float* blast;
   int K_last;
   int use_tanh;
-  float sA;
+  float sA, sD;                    // activation / gradient operand scales
   int first_append;                // layer 0's output gets xyz appended (latent_in == 1)
+};
+
+struct TcIO {
+  const float* points; int64_t n_host; const int32_t* n_dev; float clamp_dist;
+  float* sdf; float* grad; const float* coef; const uint8_t* use_clamp; float* acc0; float* accl;
+  int64_t* rows_evaluated;
 };
 
 // --------------------------------------------------------------------------------------------- PTX helpers
@@ -142,19 +153,20 @@ __device__ __forceinline__ void store_group(uint8_t* smem, int feat0, int row, c
 }
 
 // --------------------------------------------------------------------------------------------- kernel
+// MODE 0: forward (sdf).  MODE 1: forward + transposed chain -> d clamp(sdf)/d xyz.  MODE 2: backward replay with per-row
+// upstream coefficients: d/dxyz per row and the row-summed pre-activation gradients of layer 0 / the latent_in layer.
+template <int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
-mlp_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P, const float* __restrict__ points,
-                  int64_t n_host, const int32_t* __restrict__ n_dev, float clamp_dist, float* __restrict__ sdf_out,
-                  int64_t* rows_evaluated) {
+mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P, const TcIO io) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  const int64_t n = n_dev ? (int64_t)*n_dev : n_host;
+  const int64_t n = io.n_dev ? (int64_t)*io.n_dev : io.n_host;
   if (n <= 0) return;
   const uint32_t rank = cluster_ctarank();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
   const int64_t n_tiles = (n + 127) / 128;
-  if (blockIdx.x == 0 && tid == 0 && rows_evaluated)
-    atomicAdd(reinterpret_cast<unsigned long long*>(rows_evaluated), (unsigned long long)n);
+  if (blockIdx.x == 0 && tid == 0 && io.rows_evaluated)
+    atomicAdd(reinterpret_cast<unsigned long long*>(io.rows_evaluated), (unsigned long long)n);
 
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bar0 = sbase + OFF_BAR;
@@ -164,6 +176,7 @@ mlp_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P, co
   auto D_FULL = [&](int b) { return bar0 + 8 * (2 * NST + 8 + b); };
   const uint32_t FIN = bar0 + 8 * (2 * NST + 10);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 8 * (2 * NST + 11));
+  const int n_prog = P.n_prog;
 
   if (tid == 0) {
     for (int s = 0; s < NST; ++s) { mbar_init(W_FULL(s), 1); mbar_init(W_EMPTY(s), 1); }
@@ -188,15 +201,14 @@ mlp_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P, co
       uint32_t it = 0;
       const uint32_t bar_leader_mask = 0xFEFFFFFFu;
       for (int64_t t = cluster_id; t < n_tiles; t += n_clusters) {
-        for (int m = 0; m < P.n_mma; ++m) {
-          const LayerTC& L = P.L[m];
-          const int nstage = L.kc32 * L.nh;
+        for (int m = 0; m < n_prog; ++m) {
+          const int nstage = P.L[m].kc32 * P.L[m].nh, sb = P.L[m].stage_base;
           for (int s = 0; s < nstage; ++s, ++it) {
             const int slot = it % NST;
             const uint32_t ph = (it / NST) & 1;
             mbar_wait(W_EMPTY(slot), ph ^ 1);
             if (rank == 0) mbar_expect_tx(W_FULL(slot), 2 * STAGE_BYTES);
-            const int row = ((L.stage_base + s) * 2 + (int)rank) * (STAGE_BYTES / 128);
+            const int row = ((sb + s) * 2 + (int)rank) * (STAGE_BYTES / 128);
             asm volatile(
                 "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
                     "r"(sbase + OFF_W + slot * STAGE_BYTES),
@@ -214,19 +226,19 @@ mlp_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P, co
       uint32_t it = 0, G = 0, a_phase = 0, fin_phase = 0;
       uint32_t d_first = 1;
       for (int64_t t = cluster_id; t < n_tiles; t += n_clusters) {
-        for (int m = 0; m < P.n_mma; ++m, ++G) {
-          const LayerTC& L = P.L[m];
+        for (int m = 0; m < n_prog; ++m, ++G) {
+          const int kc32 = P.L[m].kc32, nh = P.L[m].nh;
           const uint32_t buf = G & 1;
-          // the final-layer accumulator of the previous tile lives in this buffer until its epilogue drained it
+          // the last accumulator of the previous tile lives in this buffer until its epilogue drained it
           if (m == 1 && !d_first) { mbar_wait_cluster(FIN, fin_phase); fin_phase ^= 1; tc_fence_after(); }
-          for (int kc = 0; kc < L.kc32; ++kc) {
+          for (int kc = 0; kc < kc32; ++kc) {
             if ((kc & 1) == 0) {
               const int c = kc >> 1;
               mbar_wait_cluster(A_FULL(c), (a_phase >> c) & 1);
               a_phase ^= (1u << c);
               tc_fence_after();
             }
-            for (int h = 0; h < L.nh; ++h, ++it) {
+            for (int h = 0; h < nh; ++h, ++it) {
               const int slot = it % NST;
               mbar_wait(W_FULL(slot), (it / NST) & 1);
               tc_fence_after();
@@ -260,13 +272,18 @@ mlp_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P, co
     const int ch = ew >> 2;              // which 64-column half of those 128 this warp handles
     const int row = 32 * (qq & 1) + lane;
     const uint32_t lane_base = (uint32_t)(32 * qq) << 16;
-    const float sA = P.sA;
+    const float sA = P.sA, sD = P.sD;
+    const int n_mma = P.n_mma;
+    float* part = reinterpret_cast<float*>(smem + OFF_PART);
+    float* rowd = reinterpret_cast<float*>(smem + OFF_ROWD);
     uint32_t G = 0, d_phase = 0;
     float px = 0.f, py = 0.f, pz = 0.f;
+    uint32_t mk[DIST_MAX_LAYERS][4];     // ReLU sign bits of this thread's (row, features) per net layer (MODE >= 1)
+    float acc0r[4] = {0.f, 0.f, 0.f, 0.f}, acclr[4] = {0.f, 0.f, 0.f, 0.f};  // MODE 2: per-lane running column sums
 
     auto load_point = [&](int64_t t) {
       const int64_t gr = t * 128 + rank * 64 + row;
-      if (gr < n) { px = points[gr * 3]; py = points[gr * 3 + 1]; pz = points[gr * 3 + 2]; }
+      if (gr < n) { px = io.points[gr * 3]; py = io.points[gr * 3 + 1]; pz = io.points[gr * 3 + 2]; }
       else { px = py = pz = 0.f; }
     };
     auto signal_chunk = [&](int c) {
@@ -282,6 +299,7 @@ mlp_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P, co
         const int c = 4 * h + 2 * q + ch;
         if (c >= kchunks) continue;
         const int f0 = 64 * c;
+        uint32_t m0 = 0, m1 = 0;
 #pragma unroll 1
         for (int g = 0; g < 8; ++g) {
           float x[8];
@@ -291,7 +309,8 @@ mlp_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P, co
             float v = 0.f;
             if (f < P.N0) {
               v = fmaf(__ldg(P.w0 + 2 * P.N0p4 + f), pz, fmaf(__ldg(P.w0 + P.N0p4 + f), py, __ldg(P.w0 + f) * px)) + __ldg(P.bias0 + f);
-              v = fmaxf(v, 0.f);
+              if (v > 0.f) { if (g < 4) m0 |= 1u << (8 * g + e); else m1 |= 1u << (8 * (g - 4) + e); }
+              else v = 0.f;
             } else if (P.first_append && f < P.N0 + 3) {
               v = (f == P.N0) ? px : ((f == P.N0 + 1) ? py : pz);
             }
@@ -299,83 +318,212 @@ mlp_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P, co
           }
           store_group(smem, f0 + 8 * g, row, x);
         }
+        if (MODE != 0) { mk[0][2 * h] = m0; mk[0][2 * h + 1] = m1; }
         signal_chunk(c);
       }
+    };
+    // sum over the 32 lanes (rows) of this warp of v[j], result for column j lands in lane j  (reduce-scatter)
+    auto colsum32 = [&](float (&v)[32]) -> float {
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) {
+        const bool up = (lane & o) != 0;
+#pragma unroll
+        for (int j = 0; j < o; ++j) {
+          const float mine = up ? v[j + o] : v[j];
+          const float send = up ? v[j] : v[j + o];
+          v[j] = mine + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+      }
+      return v[0];
     };
 
     int64_t t = cluster_id;
     if (t < n_tiles) { load_point(t); layer0(); }
     for (; t < n_tiles; t += n_clusters) {
       const int64_t gr = t * 128 + rank * 64 + row;
-      float dot = 0.f;
-      for (int m = 0; m < P.n_mma; ++m, ++G) {
-        const LayerTC& L = P.L[m];
+      float dot = 0.f, rowscale = 0.f, dx = 0.f, dy = 0.f, dz = 0.f;
+      uint32_t mk0s[4] = {0u, 0u, 0u, 0u};
+      for (int m = 0; m < n_prog; ++m, ++G) {
         const uint32_t buf = G & 1;
-        const bool is_last = (m == P.n_mma - 1);
+        const bool fwd = m < n_mma;
+        const bool fwd_last = (m == n_mma - 1);
+        const bool prog_last = (m == n_prog - 1);
+        const int LN = P.L[m].N, Lnh = P.L[m].nh, Lapp = P.L[m].app_xyz;
+        const float cscale = P.L[m].inv_scale;
+        const float* Lbias = P.L[m].bias;
         mbar_wait(D_FULL(buf), (d_phase >> buf) & 1);
         d_phase ^= (1u << buf);
         tc_fence_after();
-        if (is_last) {
+        if (prog_last) {
           // all MMAs of this tile are complete: A is free -> start the next tile's layer 0 before draining D
+          if (MODE != 0) { mk0s[0] = mk[0][0]; mk0s[1] = mk[0][1]; mk0s[2] = mk[0][2]; mk0s[3] = mk[0][3]; }
           if (t + n_clusters < n_tiles) { load_point(t + n_clusters); layer0(); }
         }
-        const int kchunks_next = is_last ? 0 : (P.L[m + 1].kc32 >> 1);
-        const float cscale = L.inv_scale;
-        for (int h = 0; h < L.nh; ++h) {
+        const int kchunks_next = prog_last ? 0 : (P.L[m + 1].kc32 >> 1);
+        // net layer whose ReLU mask gates the values produced here (transposed chain): l-1 with l = 2 n_mma - m
+        const int mask_layer = fwd ? (m + 1) : (2 * n_mma - m - 1);
+        for (int h = 0; h < Lnh; ++h) {
           const int c = 4 * h + 2 * q + ch;
           const int f0 = 256 * h + 128 * q + 64 * ch;
-          if (!is_last && c >= kchunks_next) continue;
-          if (is_last && f0 >= L.N) continue;
+          bool need_store = false, process = false;
+          if (fwd && !fwd_last) { need_store = c < kchunks_next; process = need_store; }
+          else if (fwd_last) { process = f0 < LN; }
+          else if (!prog_last) { need_store = c < kchunks_next; process = need_store || (Lapp && f0 < LN + 3 && f0 + 64 > LN); }
+          else { process = f0 < LN + 3 * Lapp; }
+          if (!process) continue;
 #pragma unroll 1
           for (int sub = 0; sub < 2; ++sub) {
             float v[32];
             tmem_ld32(tmem + lane_base + buf * 256 + h * 128 + 64 * ch + 32 * sub, v);
             const int fb = f0 + 32 * sub;
-            if (is_last) {
+            if (fwd) {
+              // ---- forward: bias + ReLU (deep_sdf_decoder.py:96,105)
+              uint32_t mb = 0;
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
                 const int f = fb + j;
-                if (f < L.N) {
-                  const float a = fmaxf(fmaf(v[j], cscale, __ldg(L.bias + f)), 0.f);
-                  dot = fmaf(a, __ldg(P.wlast + f), dot);
+                float a = 0.f;
+                if (f < LN) {
+                  a = fmaf(v[j], cscale, __ldg(Lbias + f));
+                  if (a > 0.f) mb |= 1u << j; else a = 0.f;
+                } else if (Lapp && f < LN + 3) {
+                  a = (f == LN) ? px : ((f == LN + 1) ? py : pz);
+                }
+                v[j] = a;
+              }
+              if (MODE != 0) mk[m + 1][2 * h + sub] = mb;
+              if (fwd_last) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (fb + j < LN) dot = fmaf(v[j], __ldg(P.wlast + fb + j), dot);
+              } else if (need_store) {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                  float x[8];
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) x[e] = v[8 * g + e] * sA;
+                  store_group(smem, fb + 8 * g, row, x);
                 }
               }
             } else {
+              // ---- transposed chain: gradient w.r.t. the input of net layer l = 2 n_mma - m
+              const uint32_t mb = (mask_layer == 0 && prog_last) ? mk0s[2 * h + sub] : mk[mask_layer][2 * h + sub];
 #pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                float x[8];
+              for (int j = 0; j < 32; ++j) {
+                const int f = fb + j;
+                const float g = v[j] * cscale;
+                float d = 0.f;
+                if (f < LN) d = ((mb >> j) & 1u) ? g : 0.f;
+                else if (Lapp && f < LN + 3) { if (f == LN) dx += g; else if (f == LN + 1) dy += g; else dz += g; }
+                v[j] = d;
+              }
+              if (prog_last) {
+                // delta of layer 0's pre-activation: chain to xyz through W0 (K = 3, CUDA cores)
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                  const int f = fb + 8 * g + e;
-                  float a = 0.f;
-                  if (f < L.N) a = fmaxf(fmaf(v[8 * g + e], cscale, __ldg(L.bias + f)), 0.f);
-                  else if (L.app_xyz && f < L.N + 3) a = (f == L.N) ? px : ((f == L.N + 1) ? py : pz);
-                  x[e] = a * sA;
+                for (int j = 0; j < 32; ++j) {
+                  const int f = fb + j;
+                  if (f < LN) {
+                    dx = fmaf(v[j], __ldg(P.w0 + f), dx);
+                    dy = fmaf(v[j], __ldg(P.w0 + P.N0p4 + f), dy);
+                    dz = fmaf(v[j], __ldg(P.w0 + 2 * P.N0p4 + f), dz);
+                  }
                 }
-                store_group(smem, fb + 8 * g, row, x);
+              } else if (need_store) {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                  float x[8];
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) x[e] = v[8 * g + e] * sD;
+                  store_group(smem, fb + 8 * g, row, x);
+                }
+              }
+              if (MODE == 2 && (prog_last || m == P.acc_l_prog)) {
+                // row-sum of rowscale * delta for the latent gradient; column j of this 32-block ends in lane j
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] *= rowscale;
+                const float sres = colsum32(v);
+                if (prog_last) acc0r[2 * h + sub] += sres; else acclr[2 * h + sub] += sres;
               }
             }
           }
-          if (!is_last) signal_chunk(c);
+          if (need_store) signal_chunk(c);
         }
-        if (is_last) {
-          // the accumulator of the final layer is drained: release it for the second MMA layer of the next tile
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(FIN, 0);
-          // combine the 4 partial dot products of each row (q x ch) and finish: bias, tanh (deep_sdf_decoder.py:109-110)
-          float* part = reinterpret_cast<float*>(smem + OFF_PART);
+        if (fwd_last) {
+          // combine the 4 partial dot products of each row (q x ch): bias, tanh (deep_sdf_decoder.py:109-110)
           part[row * 4 + 2 * q + ch] = dot;
           epi_bar_sync();
           if (q == 0 && ch == 0) {
-            float s = (part[row * 4] + part[row * 4 + 1]) + (part[row * 4 + 2] + part[row * 4 + 3]) + __ldg(P.blast);
-            float o = tanhf(s);
-            if (P.use_tanh) o = tanhf(o);
-            if (clamp_dist > 0.f) o = fminf(fmaxf(o, -clamp_dist), clamp_dist);
-            if (gr < n) sdf_out[gr] = o;
+            const float s = (part[row * 4] + part[row * 4 + 1]) + (part[row * 4 + 2] + part[row * 4 + 3]) + __ldg(P.blast);
+            float t1 = s, o = tanhf(s);
+            if (P.use_tanh) { t1 = o; o = tanhf(o); }
+            float oc = o;
+            if (io.clamp_dist > 0.f) oc = fminf(fmaxf(o, -io.clamp_dist), io.clamp_dist);
+            if (gr < n && io.sdf) io.sdf[gr] = oc;
+            if (MODE != 0) {
+              float d = 1.f - o * o;
+              if (P.use_tanh) d *= (1.f - t1 * t1);
+              bool uc = io.clamp_dist > 0.f;
+              if (MODE == 2 && io.use_clamp) uc = (gr < n) ? (io.use_clamp[gr] != 0) : false;
+              if (uc && !(o >= -io.clamp_dist && o <= io.clamp_dist)) d = 0.f;
+              float cf = 1.f;
+              if (MODE == 2 && io.coef) cf = (gr < n) ? io.coef[gr] : 0.f;
+              if (gr >= n) cf = 0.f;
+              rowd[row] = d * cf;
+            }
           }
           epi_bar_sync();
+          if (MODE != 0) {
+            rowscale = rowd[row];
+            // seed of the transposed chain (unit): delta[f] = w_last[f] * relu'(f), as A of the first transposed layer
+            const int kchunks = P.L[n_mma].kc32 >> 1;
+            for (int h = 0; h < Lnh; ++h) {
+              const int c = 4 * h + 2 * q + ch;
+              if (c >= kchunks) continue;
+              const int f0 = 64 * c;
+#pragma unroll 1
+              for (int g = 0; g < 8; ++g) {
+                float x[8];
+                const uint32_t mb = mk[n_mma][2 * h + (g >> 2)];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  const int f = f0 + 8 * g + e;
+                  x[e] = (f < LN && ((mb >> (8 * (g & 3) + e)) & 1u)) ? __ldg(P.wlast + f) * sD : 0.f;
+                }
+                store_group(smem, f0 + 8 * g, row, x);
+              }
+              signal_chunk(c);
+            }
+          }
         }
+        if (prog_last) {
+          // the last accumulator is drained: release it for the second layer of the next tile
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(FIN, 0);
+          if (MODE != 0) {
+            // combine the 4 partial d/dxyz of each row, scale by the row's upstream factor, write out
+            float res[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+              part[row * 4 + 2 * q + ch] = (k == 0) ? dx : ((k == 1) ? dy : dz);
+              epi_bar_sync();
+              res[k] = (part[row * 4] + part[row * 4 + 1]) + (part[row * 4 + 2] + part[row * 4 + 3]);
+              epi_bar_sync();
+            }
+            if (q == 0 && ch == 0 && gr < n && io.grad) {
+              io.grad[gr * 3] = res[0] * rowscale; io.grad[gr * 3 + 1] = res[1] * rowscale; io.grad[gr * 3 + 2] = res[2] * rowscale;
+            }
+          }
+        }
+      }
+    }
+    if (MODE == 2) {
+      // flush the per-lane running column sums: lane j of this warp holds columns f0 + 32 sub + j of its chunks
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int f = 256 * (i >> 1) + 128 * q + 64 * ch + 32 * (i & 1) + lane;
+        if (io.acc0 && f < P.N0 && acc0r[i] != 0.f) atomicAdd(io.acc0 + f, acc0r[i]);
+        if (io.accl && P.acc_l_prog >= 0 && f < P.accl_N && acclr[i] != 0.f) atomicAdd(io.accl + f, acclr[i]);
       }
     }
   }
@@ -404,7 +552,7 @@ EncodeFn get_encode() {
 }  // namespace
 
 int mlp_tc_launch(const dist_net_t* net, const NetDev& nd, int mode, const MlpArgs& a, cudaStream_t stream) {
-  if (mode != 0) return mlp_simt_launch(nd, mode, a, stream);  // gradient chains: fp32 engine (for now)
+  DIST_REQUIRE(mode >= 0 && mode <= 2, "tensor-core engine: bad mode %d", mode);
   DIST_REQUIRE(net->tc_blob && net->tc_scale, "tensor-core engine: operands not prepared (tc.prepare)");
   const int nl = nd.n_layers;
   DIST_REQUIRE(nl >= 4 && nl <= 10, "tensor-core engine: %d layers unsupported", nl);
@@ -415,8 +563,10 @@ int mlp_tc_launch(const dist_net_t* net, const NetDev& nd, int mode, const MlpAr
   TcParams P;
   memset(&P, 0, sizeof(P));
   P.n_mma = nl - 2;
+  P.n_prog = (mode == 0) ? P.n_mma : 2 * P.n_mma;
+  P.acc_l_prog = -1;
   int stage = 0;
-  for (int m = 0; m < P.n_mma; ++m) {
+  for (int m = 0; m < P.n_mma; ++m) {   // forward layers: net layer l = m + 1
     const int l = m + 1;
     LayerTC& L = P.L[m];
     L.kc32 = round_up(nd.K[l], 64) / 32;
@@ -429,10 +579,30 @@ int mlp_tc_launch(const dist_net_t* net, const NetDev& nd, int mode, const MlpAr
     L.bias = nd.bias[l];
     DIST_REQUIRE(nd.N[l] + 3 * L.app_xyz <= 256 * L.nh && nd.N[l] <= 512, "tensor-core engine: layer %d width unsupported", l);
   }
+  for (int j = 0; j < P.n_mma; ++j) {   // transposed chain: net layer l = n_mma - j, B operand = W_l^T
+    const int l = P.n_mma - j;
+    LayerTC& L = P.L[P.n_mma + j];
+    L.kc32 = round_up(nd.N[l], 64) / 32;
+    L.nh = (nd.K[l] + 255) / 256;
+    L.stage_base = stage;
+    stage += L.kc32 * L.nh;
+    L.N = nd.N[l - 1];
+    L.app_xyz = (l == nd.latent_in) ? 1 : 0;
+    L.inv_scale = net->tc_scale[P.n_mma + j];
+    L.bias = nullptr;
+    if (l - 1 == nd.latent_in) P.acc_l_prog = P.n_mma + j;   // this layer produces delta of the latent_in layer
+  }
+  DIST_REQUIRE((int64_t)stage * 2 * STAGE_BYTES == net->tc_blob_bytes, "tensor-core engine: operand blob size mismatch");
+  P.accl_N = (nd.latent_in >= 0) ? nd.N[nd.latent_in] : 0;
   P.w0 = nd.Wt[0]; P.bias0 = nd.bias[0]; P.N0 = nd.N[0]; P.N0p4 = round_up(nd.N[0], 4);
   P.wlast = nd.W[nl - 1]; P.blast = nd.bias[nl - 1]; P.K_last = nd.K[nl - 1];
-  P.use_tanh = nd.use_tanh; P.sA = 32.0f;
+  P.use_tanh = nd.use_tanh; P.sA = 32.0f; P.sD = 256.0f;
   P.first_append = (nd.latent_in == 1) ? 1 : 0;
+
+  TcIO io;
+  io.points = a.points; io.n_host = a.n_host; io.n_dev = a.n_dev; io.clamp_dist = a.clamp_dist;
+  io.sdf = a.sdf; io.grad = a.grad; io.coef = a.coef; io.use_clamp = a.use_clamp; io.acc0 = a.acc0; io.accl = a.accl;
+  io.rows_evaluated = a.rows_evaluated;
 
   // tensor map over the blob: rows of 128 B; one box = one 16 KB stage of one CTA
   CUtensorMap tmap;
@@ -448,15 +618,19 @@ int mlp_tc_launch(const dist_net_t* net, const NetDev& nd, int mode, const MlpAr
 
   static bool attr_done = false;
   if (!attr_done) {
-    DIST_CHECK_CUDA(cudaFuncSetAttribute(mlp_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    DIST_CHECK_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    DIST_CHECK_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    DIST_CHECK_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr_done = true;
   }
   const int64_t tiles = (a.n_host + 127) / 128;
   int clusters = num_sms() / 2;
   if (tiles < clusters) clusters = (int)tiles;
   if (clusters < 1) clusters = 1;
-  mlp_tc_fwd_kernel<<<clusters * 2, NTHREADS, SMEM_BYTES, stream>>>(tmap, P, a.points, a.n_host, a.n_dev, a.clamp_dist, a.sdf,
-                                                                   a.rows_evaluated); count_launch();
+  if (mode == 0) { mlp_tc_kernel<0><<<clusters * 2, NTHREADS, SMEM_BYTES, stream>>>(tmap, P, io); }
+  else if (mode == 1) { mlp_tc_kernel<1><<<clusters * 2, NTHREADS, SMEM_BYTES, stream>>>(tmap, P, io); }
+  else { mlp_tc_kernel<2><<<clusters * 2, NTHREADS, SMEM_BYTES, stream>>>(tmap, P, io); }
+  count_launch();
   DIST_CHECK_CUDA(cudaGetLastError());
   return DIST_OK;
 }

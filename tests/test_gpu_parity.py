@@ -40,7 +40,8 @@ def test_decoder_points_golden(engine):
     assert gu.rel(grad.cpu()[keep], torch.from_numpy(gold["grad"])[keep]) < 1e-5
 
 
-def test_decode_sdf_autograd():
+@pytest.mark.parametrize("engine", ["simt", "tc"])
+def test_decode_sdf_autograd(engine):
     """decode_sdf is differentiable w.r.t. latent and points like the reference's (decoder_utils.py:53)."""
     from oracle.sdf_oracle import decode_sdf as o_decode
     dec_c, dec_g = cases.decoder("B"), gu.gpu_decoder("B")
@@ -52,7 +53,7 @@ def test_decode_sdf_autograd():
     (o_decode(dec_c, lat_c, p_c, clamp_dist=0.1) * w).sum().backward()
     lat_g = cases.synth.make_latent().cuda().requires_grad_(True)
     p_g = pts.cuda().requires_grad_(True)
-    (pkg.decode_sdf(dec_g, lat_g, p_g, clamp_dist=0.1, engine="simt") * w.cuda()).sum().backward()
+    (pkg.decode_sdf(dec_g, lat_g, p_g, clamp_dist=0.1, engine=engine) * w.cuda()).sum().backward()
     assert gu.rel(lat_g.grad, lat_c.grad) < 1e-4
     assert gu.rel(p_g.grad, p_c.grad) < 1e-4
 
@@ -126,6 +127,37 @@ def test_tc_engine_matches_simt_at_scale():
     # engine 'auto' resolves to the tensor-core engine for the standard spec on sm_100
     c = pkg.decode_sdf(dec, lat, pts[:1000], clamp_dist=None)
     assert torch.equal(c, b[:1000])
+
+
+def test_tc_gradient_modes_match_simt_at_scale():
+    """Input-gradient and backward-replay kernels of the tensor-core engine vs the fp32 SIMT engine, 200 K rows."""
+    dec = gu.gpu_decoder("B")
+    lat = cases.synth.make_latent().cuda()
+    g = torch.Generator().manual_seed(8)
+    n = 200003
+    pts = ((torch.rand(n, 3, generator=g) - 0.5) * 1.4).cuda()
+    ga = pkg.decode_sdf_gradient(dec, lat, pts, clamp_dist=0.1, engine="simt")
+    gb = pkg.decode_sdf_gradient(dec, lat, pts, clamp_dist=0.1, engine="tc")
+    err = (ga - gb).norm(dim=1)
+    flips = int((err > 1e-3).sum())
+    assert flips <= max(3, n // 2000), flips                   # ReLU-boundary flips only
+    keep = err <= 1e-3
+    assert gu.rel(gb[keep], ga[keep]) < 2e-6
+    # positive row weights: a randomly signed sum over 200 K rows cancels to ~1/450 of its terms, so that a handful
+    # of ReLU-boundary rows (present in ANY two fp32 evaluations: the fp32 oracle itself sits 2e-4..6e-4 from its fp64
+    # twin on such a sum) would dominate the comparison
+    w = torch.rand(n, 1, generator=g).cuda() + 0.1
+    res = {}
+    for eng in ("simt", "tc"):
+        l = lat.clone().requires_grad_(True)
+        p = pts.clone().requires_grad_(True)
+        (pkg.decode_sdf(dec, l, p, clamp_dist=0.1, engine=eng) * w).sum().backward()
+        res[eng] = (l.grad.clone(), p.grad.clone())
+    assert gu.rel(res["tc"][0], res["simt"][0]) < 3e-4          # d/dlatent: sums over 200 K rows incl. flipped ones
+    e2 = (res["tc"][1] - res["simt"][1]).norm(dim=1)
+    k2 = e2 <= 1e-3 * w.abs().reshape(-1).clamp(min=1e-3)
+    assert int((~k2).sum()) <= max(3, n // 2000)
+    assert gu.rel(res["tc"][1][k2], res["simt"][1][k2]) < 2e-6
 
 
 def test_tc_engine_ragged_counts_and_clamp():
