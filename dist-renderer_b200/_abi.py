@@ -27,7 +27,8 @@ class Net(C.Structure):
                 ("use_tanh", C.c_int32), ("K", C.c_int32 * MAX_LAYERS), ("N", C.c_int32 * MAX_LAYERS),
                 ("Wt", C.c_void_p * MAX_LAYERS), ("W", C.c_void_p * MAX_LAYERS), ("bias", C.c_void_p * MAX_LAYERS),
                 ("Wz0", C.c_void_p), ("b0", C.c_void_p), ("Wzl", C.c_void_p), ("bl", C.c_void_p),
-                ("tc_blob", C.c_void_p), ("tc_scale", C.c_void_p), ("tc_blob_bytes", C.c_int64)]
+                ("tc_blob", C.c_void_p), ("tc_scale", C.c_void_p), ("tc_blob_bytes", C.c_int64),
+                ("tc_bias", C.c_void_p * MAX_LAYERS)]
 
 
 class Camera(C.Structure):

@@ -138,6 +138,25 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, float (&v)[64]) {
+  uint32_t r[64];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x64.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,"
+      "%23,%24,%25,%26,%27,%28,%29,%30,%31,%32,%33,%34,%35,%36,%37,%38,%39,%40,%41,%42,%43,%44,%45,%46,%47,%48,%49,%50,%51,%52,"
+      "%53,%54,%55,%56,%57,%58,%59,%60,%61,%62,%63}, [%64];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]), "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]),
+        "=r"(r[37]), "=r"(r[38]), "=r"(r[39]), "=r"(r[40]), "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]),
+        "=r"(r[46]), "=r"(r[47]), "=r"(r[48]), "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]),
+        "=r"(r[55]), "=r"(r[56]), "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 // Writes 8 consecutive features (one K-group panel row) of this thread's row: x[] already multiplied by sA.
 __device__ __forceinline__ void store_group(uint8_t* smem, int feat0, int row, const float* x) {
   __half2 h[4], l[4];
@@ -371,77 +390,114 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P, const 
           else if (!prog_last) { need_store = c < kchunks_next; process = need_store || (Lapp && f0 < LN + 3 && f0 + 64 > LN); }
           else { process = f0 < LN + 3 * Lapp; }
           if (!process) continue;
-#pragma unroll 1
-          for (int sub = 0; sub < 2; ++sub) {
-            float v[32];
-            tmem_ld32(tmem + lane_base + buf * 256 + h * 128 + 64 * ch + 32 * sub, v);
-            const int fb = f0 + 32 * sub;
-            if (fwd) {
-              // ---- forward: bias + ReLU (deep_sdf_decoder.py:96,105)
-              uint32_t mb = 0;
+          float v[64];
+          tmem_ld64(tmem + lane_base + buf * 256 + h * 128 + 64 * ch, v);
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const int f = fb + j;
-                float a = 0.f;
-                if (f < LN) {
-                  a = fmaf(v[j], cscale, __ldg(Lbias + f));
-                  if (a > 0.f) mb |= 1u << j; else a = 0.f;
-                } else if (Lapp && f < LN + 3) {
-                  a = (f == LN) ? px : ((f == LN + 1) ? py : pz);
+          for (int sub = 0; sub < 2; ++sub) {
+            const int fb = f0 + 32 * sub;
+            const bool interior = (fb + 32 <= LN);            // warp-uniform: no per-element bounds checks
+            if (fwd) {
+              // ---- forward: bias + ReLU (deep_sdf_decoder.py:96,105); values are carried in units of sA
+              uint32_t mb = 0;
+              if (interior) {
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) {
+                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(Lbias + fb) + j4);
+                  const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const int j = 32 * sub + 4 * j4 + e;
+                    const float a = fmaf(v[j], cscale, bb[e]);
+                    if (MODE != 0) mb |= (a > 0.f) ? (1u << (4 * j4 + e)) : 0u;
+                    v[j] = fmaxf(a, 0.f);
+                  }
                 }
-                v[j] = a;
+              } else {
+#pragma unroll
+                for (int jj = 0; jj < 32; ++jj) {
+                  const int j = 32 * sub + jj, f = fb + jj;
+                  float a = 0.f;
+                  if (f < LN) {
+                    a = fmaf(v[j], cscale, __ldg(Lbias + f));
+                    if (a > 0.f) mb |= 1u << jj; else a = 0.f;
+                  } else if (Lapp && f < LN + 3) {
+                    a = ((f == LN) ? px : ((f == LN + 1) ? py : pz)) * sA;
+                  }
+                  v[j] = a;
+                }
               }
               if (MODE != 0) mk[m + 1][2 * h + sub] = mb;
               if (fwd_last) {
+                if (interior) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
-                  if (fb + j < LN) dot = fmaf(v[j], __ldg(P.wlast + fb + j), dot);
+                  for (int j4 = 0; j4 < 8; ++j4) {
+                    const float4 w4 = __ldg(reinterpret_cast<const float4*>(P.wlast + fb) + j4);
+                    dot = fmaf(v[32 * sub + 4 * j4], w4.x, dot); dot = fmaf(v[32 * sub + 4 * j4 + 1], w4.y, dot);
+                    dot = fmaf(v[32 * sub + 4 * j4 + 2], w4.z, dot); dot = fmaf(v[32 * sub + 4 * j4 + 3], w4.w, dot);
+                  }
+                } else {
+#pragma unroll
+                  for (int jj = 0; jj < 32; ++jj)
+                    if (fb + jj < LN) dot = fmaf(v[32 * sub + jj], __ldg(P.wlast + fb + jj), dot);
+                }
               } else if (need_store) {
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                  float x[8];
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) x[e] = v[8 * g + e] * sA;
-                  store_group(smem, fb + 8 * g, row, x);
-                }
+                for (int g = 0; g < 4; ++g) store_group(smem, fb + 8 * g, row, &v[32 * sub + 8 * g]);
               }
             } else {
-              // ---- transposed chain: gradient w.r.t. the input of net layer l = 2 n_mma - m
+              // ---- transposed chain: gradient w.r.t. the input of net layer l = 2 n_mma - m (units of sD)
               const uint32_t mb = (mask_layer == 0 && prog_last) ? mk0s[2 * h + sub] : mk[mask_layer][2 * h + sub];
+              if (interior) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const int f = fb + j;
-                const float g = v[j] * cscale;
-                float d = 0.f;
-                if (f < LN) d = ((mb >> j) & 1u) ? g : 0.f;
-                else if (Lapp && f < LN + 3) { if (f == LN) dx += g; else if (f == LN + 1) dy += g; else dz += g; }
-                v[j] = d;
+                for (int jj = 0; jj < 32; ++jj) {
+                  const int j = 32 * sub + jj;
+                  v[j] = ((mb >> jj) & 1u) ? v[j] * cscale : 0.f;
+                }
+              } else {
+#pragma unroll
+                for (int jj = 0; jj < 32; ++jj) {
+                  const int j = 32 * sub + jj, f = fb + jj;
+                  const float g = v[j] * cscale;
+                  float d = 0.f;
+                  if (f < LN) d = ((mb >> jj) & 1u) ? g : 0.f;
+                  else if (Lapp && f < LN + 3) { if (f == LN) dx += g; else if (f == LN + 1) dy += g; else dz += g; }
+                  v[j] = d;
+                }
               }
               if (prog_last) {
                 // delta of layer 0's pre-activation: chain to xyz through W0 (K = 3, CUDA cores)
+                if (interior) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                  const int f = fb + j;
-                  if (f < LN) {
-                    dx = fmaf(v[j], __ldg(P.w0 + f), dx);
-                    dy = fmaf(v[j], __ldg(P.w0 + P.N0p4 + f), dy);
-                    dz = fmaf(v[j], __ldg(P.w0 + 2 * P.N0p4 + f), dz);
+                  for (int j4 = 0; j4 < 8; ++j4) {
+                    const float4 wx = __ldg(reinterpret_cast<const float4*>(P.w0 + fb) + j4);
+                    const float4 wy = __ldg(reinterpret_cast<const float4*>(P.w0 + P.N0p4 + fb) + j4);
+                    const float4 wz = __ldg(reinterpret_cast<const float4*>(P.w0 + 2 * P.N0p4 + fb) + j4);
+                    const int j = 32 * sub + 4 * j4;
+                    dx = fmaf(v[j], wx.x, dx); dx = fmaf(v[j + 1], wx.y, dx); dx = fmaf(v[j + 2], wx.z, dx); dx = fmaf(v[j + 3], wx.w, dx);
+                    dy = fmaf(v[j], wy.x, dy); dy = fmaf(v[j + 1], wy.y, dy); dy = fmaf(v[j + 2], wy.z, dy); dy = fmaf(v[j + 3], wy.w, dy);
+                    dz = fmaf(v[j], wz.x, dz); dz = fmaf(v[j + 1], wz.y, dz); dz = fmaf(v[j + 2], wz.z, dz); dz = fmaf(v[j + 3], wz.w, dz);
+                  }
+                } else {
+#pragma unroll
+                  for (int jj = 0; jj < 32; ++jj) {
+                    const int f = fb + jj;
+                    if (f < LN) {
+                      dx = fmaf(v[32 * sub + jj], __ldg(P.w0 + f), dx);
+                      dy = fmaf(v[32 * sub + jj], __ldg(P.w0 + P.N0p4 + f), dy);
+                      dz = fmaf(v[32 * sub + jj], __ldg(P.w0 + 2 * P.N0p4 + f), dz);
+                    }
                   }
                 }
               } else if (need_store) {
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                  float x[8];
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) x[e] = v[8 * g + e] * sD;
-                  store_group(smem, fb + 8 * g, row, x);
-                }
+                for (int g = 0; g < 4; ++g) store_group(smem, fb + 8 * g, row, &v[32 * sub + 8 * g]);
               }
               if (MODE == 2 && (prog_last || m == P.acc_l_prog)) {
                 // row-sum of rowscale * delta for the latent gradient; column j of this 32-block ends in lane j
+                float w32[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] *= rowscale;
-                const float sres = colsum32(v);
+                for (int jj = 0; jj < 32; ++jj) w32[jj] = v[32 * sub + jj] * rowscale;
+                const float sres = colsum32(w32);
                 if (prog_last) acc0r[2 * h + sub] += sres; else acclr[2 * h + sub] += sres;
               }
             }
@@ -453,7 +509,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P, const 
           part[row * 4 + 2 * q + ch] = dot;
           epi_bar_sync();
           if (q == 0 && ch == 0) {
-            const float s = (part[row * 4] + part[row * 4 + 1]) + (part[row * 4 + 2] + part[row * 4 + 3]) + __ldg(P.blast);
+            const float s = ((part[row * 4] + part[row * 4 + 1]) + (part[row * 4 + 2] + part[row * 4 + 3])) * (1.f / sA) + __ldg(P.blast);
             float t1 = s, o = tanhf(s);
             if (P.use_tanh) { t1 = o; o = tanhf(o); }
             float oc = o;
@@ -511,7 +567,8 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P, const 
               epi_bar_sync();
             }
             if (q == 0 && ch == 0 && gr < n && io.grad) {
-              io.grad[gr * 3] = res[0] * rowscale; io.grad[gr * 3 + 1] = res[1] * rowscale; io.grad[gr * 3 + 2] = res[2] * rowscale;
+              const float rs = rowscale * (1.f / sD);
+              io.grad[gr * 3] = res[0] * rs; io.grad[gr * 3 + 1] = res[1] * rs; io.grad[gr * 3 + 2] = res[2] * rs;
             }
           }
         }
@@ -522,8 +579,8 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P, const 
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int f = 256 * (i >> 1) + 128 * q + 64 * ch + 32 * (i & 1) + lane;
-        if (io.acc0 && f < P.N0 && acc0r[i] != 0.f) atomicAdd(io.acc0 + f, acc0r[i]);
-        if (io.accl && P.acc_l_prog >= 0 && f < P.accl_N && acclr[i] != 0.f) atomicAdd(io.accl + f, acclr[i]);
+        if (io.acc0 && f < P.N0 && acc0r[i] != 0.f) atomicAdd(io.acc0 + f, acc0r[i] * (1.f / sD));
+        if (io.accl && P.acc_l_prog >= 0 && f < P.accl_N && acclr[i] != 0.f) atomicAdd(io.accl + f, acclr[i] * (1.f / sD));
       }
     }
   }
@@ -576,7 +633,8 @@ int mlp_tc_launch(const dist_net_t* net, const NetDev& nd, int mode, const MlpAr
     L.N = nd.N[l];
     L.app_xyz = (l + 1 == nd.latent_in) ? 1 : 0;
     L.inv_scale = net->tc_scale[m];
-    L.bias = nd.bias[l];
+    L.bias = net->tc_bias[l];
+    DIST_REQUIRE(L.bias != nullptr, "tensor-core engine: scaled bias missing for layer %d", l);
     DIST_REQUIRE(nd.N[l] + 3 * L.app_xyz <= 256 * L.nh && nd.N[l] <= 512, "tensor-core engine: layer %d width unsupported", l);
   }
   for (int j = 0; j < P.n_mma; ++j) {   // transposed chain: net layer l = n_mma - j, B operand = W_l^T

@@ -37,11 +37,7 @@ class _DecodeFn(torch.autograd.Function):
     def forward(ctx, latent, points, plan, clamp_dist, engine):
         lib = _abi.lib()
         st = _stream()
-        b0, bl, lat = plan.fold(latent, st)
-        if engine == _abi.ENGINE_TC:
-            from . import tc
-            tc.prepare(plan)
-        net = plan.c_net(b0, bl)
+        net, _keep = plan.net_for(latent, engine, st)
         pts = points.detach().float().contiguous()
         n = pts.shape[0]
         sdf = torch.empty(n, 1, device=pts.device, dtype=torch.float32)
@@ -57,8 +53,7 @@ class _DecodeFn(torch.autograd.Function):
     def backward(ctx, g):
         pts, latent = ctx.saved_tensors
         plan, lib, st = ctx.plan, _abi.lib(), _stream()
-        b0, bl, _ = plan.fold(latent if ctx.has_latent else None, st)
-        net = plan.c_net(b0, bl)
+        net, _keep = plan.net_for(latent if ctx.has_latent else None, ctx.engine, st)
         n = pts.shape[0]
         coef = g.detach().reshape(-1).float().contiguous()
         dpts = torch.zeros(n, 3, device=pts.device)
@@ -101,11 +96,7 @@ def decode_sdf_gradient(decoder, latent_vector, points, clamp_dist=0.1, MAX_POIN
     plan = plan_for(decoder)
     eng = resolve_engine(plan, engine or DEFAULT_ENGINE)
     st = _stream()
-    b0, bl, _ = plan.fold(latent_vector, st)
-    if eng == _abi.ENGINE_TC:
-        from . import tc
-        tc.prepare(plan)
-    net = plan.c_net(b0, bl)
+    net, _keep = plan.net_for(latent_vector, eng, st)
     pts = points.detach().float().contiguous()
     n = pts.shape[0]
     grad = torch.empty(n, 3, device=pts.device)

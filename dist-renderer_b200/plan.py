@@ -128,7 +128,21 @@ class DecoderPlan(object):
         _abi.check(lib.dist_fold_latent(net, _abi.ptr(lat), _abi.ptr(out0), _abi.ptr(outl), stream))
         return out0, outl, lat
 
-    def c_net(self, bias0, biasl):
+    def net_for(self, latent, engine, stream):
+        """(dist_net_t, keepalive) for one call: prepares the tensor-core operands when that engine is selected,
+        folds the latent into the per-render biases and fills the descriptor."""
+        if engine == _abi.ENGINE_TC:
+            from . import tc
+            tc.prepare(self)
+        b0, bl, lat = self.fold(latent, stream)
+        bl_tc = None
+        if engine == _abi.ENGINE_TC and bl is not None:
+            from . import tc
+            bl_tc = bl * tc.S_ACT
+        net = self.c_net(b0, bl, bl_tc)
+        return net, (b0, bl, bl_tc, lat)
+
+    def c_net(self, bias0, biasl, biasl_tc=None):
         """ctypes dist_net_t for one call; bias0/biasl are the folded biases (or None before folding)."""
         net = _abi.Net()
         net.n_layers, net.latent_size, net.latent_in, net.use_tanh = self.n_layers, self.latent_size, \
@@ -151,6 +165,11 @@ class DecoderPlan(object):
             net.tc_blob = self.tc["blob"].data_ptr()
             net.tc_scale = ctypes.addressof(self.tc["inv_scale"])
             net.tc_blob_bytes = self.tc["blob"].numel() * self.tc["blob"].element_size()
+            for l in range(self.n_layers):
+                b = self.tc["bias_s"][l]
+                if l == self.latent_in and biasl_tc is not None:
+                    b = biasl_tc
+                net.tc_bias[l] = b.data_ptr()
         return net
 
     def latent_grad(self, acc0, accl):

@@ -41,11 +41,7 @@ class _RenderDepthFn(torch.autograd.Function):
         dev = ren.device
         P, B = ren.P, ren.buffer_size
         engine = resolve_engine(plan, opts["engine"])
-        if engine == _abi.ENGINE_TC:
-            from . import tc
-            tc.prepare(plan)
-        b0, bl, _ = plan.fold(latent, st)
-        net = plan.c_net(b0, bl)
+        net, _keep = plan.net_for(latent, engine, st)
         Rd = R.detach().float().contiguous()
         cam_pos = torch.matmul(-Rd.t(), T.detach().float()[:, None]).squeeze(1).contiguous()  # renderer.py:186
         cam = ren._c_camera(Rd, cam_pos, opts["use_transform"])
@@ -81,8 +77,7 @@ class _RenderDepthFn(torch.autograd.Function):
         latent, Rd, Td = ctx.saved_tensors
         ren, opts, lib, st = ctx.ren, ctx.opts, _abi.lib(), _stream()
         plan, dev, P, B = ren.plan, ren.device, ren.P, ren.buffer_size
-        b0, bl, _ = plan.fold(latent, st)
-        net = plan.c_net(b0, bl)
+        net, _keep = plan.net_for(latent, ctx.engine, st)
         cam_pos = torch.matmul(-Rd.t(), Td[:, None]).squeeze(1).contiguous()
         cam = ren._c_camera(Rd, cam_pos, opts["use_transform"])
         scr = ren._scratch()
@@ -319,11 +314,7 @@ class SDFRenderer(object):
         plan = self.plan
         plan.refresh()
         engine = resolve_engine(plan, self.engine)
-        if engine == _abi.ENGINE_TC:
-            from . import tc
-            tc.prepare(plan)
-        b0, bl, _ = plan.fold(latent, st)
-        net = plan.c_net(b0, bl)
+        net, _keep = plan.net_for(latent, engine, st)
         Rd = R.detach().float().contiguous()
         cam_pos = torch.matmul(-Rd.t(), T.detach().float()[:, None]).squeeze(1).contiguous()
         cam = self._c_camera(Rd, cam_pos, use_transform)

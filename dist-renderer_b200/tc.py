@@ -96,6 +96,7 @@ def calibrate(plan, n_points=8192):
     pts = ((torch.rand(n_points, 3, generator=g) - 0.5) * 1.2).to(plan.device)
     lat = torch.zeros(plan.latent_size, device=plan.device) if plan.latent_size > 0 else None
     b0, bl, _ = plan.fold(lat, st)
+    bl_tc = bl * S_ACT if bl is not None else None
     ref = torch.empty(n_points, device=plan.device)
     saved = plan.tc
     plan.tc = None
@@ -105,8 +106,8 @@ def calibrate(plan, n_points=8192):
     def probe(c):
         plan.tc = _build(plan, c)
         out = torch.empty(n_points, device=plan.device)
-        _abi.check(lib.dist_decoder_forward(plan.c_net(b0, bl), _abi.ENGINE_TC, _abi.ptr(pts), n_points, None, 0.0,
-                                            _abi.ptr(out), st))
+        _abi.check(lib.dist_decoder_forward(plan.c_net(b0, bl, bl_tc), _abi.ENGINE_TC, _abi.ptr(pts), n_points, None,
+                                            0.0, _abi.ptr(out), st))
         return float((out.double() - ref.double()).mean())
     c1 = 4.0e-8
     e0, e1 = probe(0.0), probe(c1)
@@ -139,7 +140,7 @@ def _build(plan, c_trunc):
         s = _pow2_scale(w)
         b, kc, nh = _tiles(w, s, c_trunc)
         blobs.append(b)
-        meta.append([kc, nh, stage, 1.0 / (S_ACT * s)])
+        meta.append([kc, nh, stage, 1.0 / s])
         stage += kc * nh
     # transposed chain: gradient w.r.t. the input of net layer l (l = n-2 .. 1): B operand = W_l^T  ([K_l, N_l])
     for l in range(n - 2, 0, -1):
@@ -147,11 +148,13 @@ def _build(plan, c_trunc):
         s = _pow2_scale(w)
         b, kc, nh = _tiles(w, s, c_trunc)
         blobs.append(b)
-        meta.append([kc, nh, stage, 1.0 / (S_GRAD * s)])
+        meta.append([kc, nh, stage, 1.0 / s])
         stage += kc * nh
     blob = torch.cat(blobs).contiguous()
     assert blob.numel() * 2 == stage * 2 * 16384
     # meta as float tensor rows: kc, nh, stage_base, inv_scale  (read on the host side of the C ABI only)
     import ctypes
     inv = (ctypes.c_float * len(meta))(*[m[3] for m in meta])   # HOST array read by the launch code of the C ABI
-    return {"blob": blob, "inv_scale": inv, "meta": meta, "n_fwd": n - 2, "stages": stage, "c_trunc": c_trunc}
+    bias_s = [b * S_ACT for b in plan.bias]   # activations are carried in units of S_ACT (ReLU is positively homogeneous)
+    return {"blob": blob, "inv_scale": inv, "meta": meta, "n_fwd": n - 2, "stages": stage, "c_trunc": c_trunc,
+            "bias_s": bias_s}

@@ -69,8 +69,9 @@ typedef struct dist_net {
   const float* bl;            /* unfolded bias of the latent_in layer */
   /* tensor-core engine operands (NULL when only the SIMT engine is prepared) */
   const void* tc_blob;        /* split-fp16 weight tiles, see csrc/mlp_tc.cu */
-  const float* tc_scale;      /* HOST array: 1/(sA*sW) per tensor-core layer (forward layers, then the transposed chain) */
+  const float* tc_scale;      /* HOST array: 1/sW per tensor-core layer (forward layers, then the transposed chain) */
   int64_t tc_blob_bytes;
+  const float* tc_bias[DIST_MAX_LAYERS]; /* biases in the engine's scaled activation units (bias * 32), per net layer */
 } dist_net_t;
 
 /* Camera + image description for one render (renderer.py:13-59,180-200). */
