@@ -20,6 +20,8 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include "common.cuh"
 
@@ -62,12 +64,14 @@ struct TcParams {
   int use_tanh;
   float sA, sD;                    // activation / gradient operand scales
   int first_append;                // layer 0's output gets xyz appended (latent_in == 1)
+  int dbg;                         // timing experiments only (DIST_TC_DEBUG): bit0 skip W_FULL waits, bit1 skip A_FULL waits
 };
 
 struct TcIO {
   const float* points; int64_t n_host; const int32_t* n_dev; float clamp_dist;
   float* sdf; float* grad; const float* coef; const uint8_t* use_clamp; float* acc0; float* accl;
   int64_t* rows_evaluated;
+  long long* dbg_out;   // DIST_TC_DEBUG bit2: [cycles, ns] of CTA 0
 };
 
 // --------------------------------------------------------------------------------------------- PTX helpers
@@ -118,6 +122,11 @@ __device__ __forceinline__ void commit_mc(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
                "h"((uint16_t)3)
                : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -187,19 +196,21 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P, const 
   if (blockIdx.x == 0 && tid == 0 && io.rows_evaluated)
     atomicAdd(reinterpret_cast<unsigned long long*>(io.rows_evaluated), (unsigned long long)n);
 
+  long long dbg_c0 = 0, dbg_t0 = 0;
+  if (io.dbg_out && blockIdx.x == 0 && tid == 0) { dbg_c0 = clock64(); asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0)); }
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bar0 = sbase + OFF_BAR;
   auto W_FULL = [&](int s) { return bar0 + 8 * s; };
   auto W_EMPTY = [&](int s) { return bar0 + 8 * (NST + s); };
   auto A_FULL = [&](int c) { return bar0 + 8 * (2 * NST + c); };
-  auto D_FULL = [&](int b) { return bar0 + 8 * (2 * NST + 8 + b); };
-  const uint32_t FIN = bar0 + 8 * (2 * NST + 10);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 8 * (2 * NST + 11));
+  auto D_FULL = [&](int b) { return bar0 + 8 * (2 * NST + 16 + b); };
+  const uint32_t FIN = bar0 + 8 * (2 * NST + 18);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 8 * (2 * NST + 19));
   const int n_prog = P.n_prog;
 
   if (tid == 0) {
     for (int s = 0; s < NST; ++s) { mbar_init(W_FULL(s), 1); mbar_init(W_EMPTY(s), 1); }
-    for (int c = 0; c < 8; ++c) mbar_init(A_FULL(c), 4);   // 2 warps x 2 CTAs produce each 64-feature chunk
+    for (int c = 0; c < 16; ++c) mbar_init(A_FULL(c), 4);  // 2 warps x 2 CTAs produce each 32-feature block
     mbar_init(D_FULL(0), 1); mbar_init(D_FULL(1), 1);
     mbar_init(FIN, 16);                                     // 8 epilogue warps x 2 CTAs
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -216,7 +227,9 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P, const 
 
   if (warp == 0) {
     // =============================================================== TMA producer (both CTAs)
-    if (lane == 0) {
+    // the whole warp runs the loop (warp-uniform control flow keeps addresses in uniform registers); one elected
+    // lane issues the copies
+    {
       uint32_t it = 0;
       const uint32_t bar_leader_mask = 0xFEFFFFFFu;
       for (int64_t t = cluster_id; t < n_tiles; t += n_clusters) {
@@ -226,22 +239,28 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P, const 
             const int slot = it % NST;
             const uint32_t ph = (it / NST) & 1;
             mbar_wait(W_EMPTY(slot), ph ^ 1);
-            if (rank == 0) mbar_expect_tx(W_FULL(slot), 2 * STAGE_BYTES);
-            const int row = ((sb + s) * 2 + (int)rank) * (STAGE_BYTES / 128);
-            asm volatile(
-                "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
-                    "r"(sbase + OFF_W + slot * STAGE_BYTES),
-                "l"(&tmap), "r"(W_FULL(slot) & bar_leader_mask), "r"(0), "r"(row)
-                : "memory");
+            if (elect_one()) {
+              if (rank == 0) mbar_expect_tx(W_FULL(slot), 2 * STAGE_BYTES);
+              const int row = ((sb + s) * 2 + (int)rank) * (STAGE_BYTES / 128);
+              asm volatile(
+                  "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
+                      "r"(sbase + OFF_W + slot * STAGE_BYTES),
+                  "l"(&tmap), "r"(W_FULL(slot) & bar_leader_mask), "r"(0), "r"(row)
+                  : "memory");
+            }
+            __syncwarp();
           }
         }
       }
     }
-    __syncwarp();
   } else if (warp == 1) {
-    // =============================================================== MMA issuer (leader CTA, one thread)
-    if (rank == 0 && lane == 0) {
+    // =============================================================== MMA issuer (leader CTA)
+    // warp-uniform loop; descriptors are advanced by adding 16-byte units to the low word; one elected lane issues
+    if (rank == 0) {
       const uint32_t idesc = (1u << 4) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
+      const uint64_t a_hi0 = make_desc(sbase + OFF_AHI, 1024, 128);
+      const uint64_t a_lo0 = make_desc(sbase + OFF_ALO, 1024, 128);
+      const uint64_t b_0 = make_desc(sbase + OFF_W, 2048, 128);
       uint32_t it = 0, G = 0, a_phase = 0, fin_phase = 0;
       uint32_t d_first = 1;
       for (int64_t t = cluster_id; t < n_tiles; t += n_clusters) {
@@ -249,40 +268,34 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P, const 
           const int kc32 = P.L[m].kc32, nh = P.L[m].nh;
           const uint32_t buf = G & 1;
           // the last accumulator of the previous tile lives in this buffer until its epilogue drained it
-          if (m == 1 && !d_first) { mbar_wait_cluster(FIN, fin_phase); fin_phase ^= 1; tc_fence_after(); }
+          if (m == 1 && !d_first) { mbar_wait_cluster(FIN, fin_phase); fin_phase ^= 1; }
           for (int kc = 0; kc < kc32; ++kc) {
-            if ((kc & 1) == 0) {
-              const int c = kc >> 1;
-              mbar_wait_cluster(A_FULL(c), (a_phase >> c) & 1);
-              a_phase ^= (1u << c);
-              tc_fence_after();
-            }
+            if (!(P.dbg & 2)) mbar_wait_cluster(A_FULL(kc), (a_phase >> kc) & 1);
+            a_phase ^= (1u << kc);
             for (int h = 0; h < nh; ++h, ++it) {
               const int slot = it % NST;
-              mbar_wait(W_FULL(slot), (it / NST) & 1);
+              if (!(P.dbg & 1)) mbar_wait(W_FULL(slot), (it / NST) & 1);
               tc_fence_after();
-              const uint32_t d_addr = tmem + buf * 256 + h * 128;
-              const uint32_t wb = sbase + OFF_W + slot * STAGE_BYTES;
+              if (elect_one()) {
+                const uint32_t d_addr = tmem + buf * 256 + h * 128;
 #pragma unroll
-              for (int ks = 0; ks < 2; ++ks) {
-                const uint32_t a_off = (uint32_t)(kc * 4 + ks * 2) * 1024;
-                const uint64_t a_hi = make_desc(sbase + OFF_AHI + a_off, 1024, 128);
-                const uint64_t a_lo = make_desc(sbase + OFF_ALO + a_off, 1024, 128);
-                const uint64_t b_hi = make_desc(wb + ks * 2 * 2048, 2048, 128);
-                const uint64_t b_lo = make_desc(wb + 8192 + ks * 2 * 2048, 2048, 128);
-                mma_f16_2cta(d_addr, a_hi, b_hi, idesc, (kc | ks) ? 1u : 0u);
-                mma_f16_2cta(d_addr, a_lo, b_hi, idesc, 1u);
-                mma_f16_2cta(d_addr, a_hi, b_lo, idesc, 1u);
+                for (int ks = 0; ks < 2; ++ks) {
+                  const uint64_t a_off = (uint64_t)((kc * 4 + ks * 2) * 64);
+                  const uint64_t b_off = (uint64_t)(slot * (STAGE_BYTES / 16) + ks * 256);
+                  mma_f16_2cta(d_addr, a_hi0 + a_off, b_0 + b_off, idesc, (kc | ks) ? 1u : 0u);
+                  mma_f16_2cta(d_addr, a_lo0 + a_off, b_0 + b_off, idesc, 1u);
+                  mma_f16_2cta(d_addr, a_hi0 + a_off, b_0 + b_off + 512, idesc, 1u);
+                }
+                commit_mc(W_EMPTY(slot));
+                if (kc == kc32 - 1 && h == nh - 1) commit_mc(D_FULL(buf));
               }
-              commit_mc(W_EMPTY(slot));
+              __syncwarp();
             }
           }
-          commit_mc(D_FULL(buf));
         }
         d_first = 0;
       }
     }
-    __syncwarp();
   } else if (warp >= 4) {
     // =============================================================== epilogue warps
     const int ew = warp - 4;
@@ -305,10 +318,10 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P, const 
       if (gr < n) { px = io.points[gr * 3]; py = io.points[gr * 3 + 1]; pz = io.points[gr * 3 + 2]; }
       else { px = py = pz = 0.f; }
     };
-    auto signal_chunk = [&](int c) {
+    auto signal_block = [&](int kc) {   // this warp's 32 rows x 32 features of A block kc are written
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(A_FULL(c), 0);
+      if (lane == 0) mbar_arrive_cluster(A_FULL(kc), 0);
     };
     // layer 0 on CUDA cores: A <- split(sA * relu(b0' + W0 xyz)), features of this thread's chunks
     auto layer0 = [&]() {
@@ -336,9 +349,9 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P, const 
             x[e] = v * sA;
           }
           store_group(smem, f0 + 8 * g, row, x);
+          if ((g & 3) == 3) signal_block(2 * c + (g >> 2));
         }
         if (MODE != 0) { mk[0][2 * h] = m0; mk[0][2 * h + 1] = m1; }
-        signal_chunk(c);
       }
     };
     // sum over the 32 lanes (rows) of this warp of v[j], result for column j lands in lane j  (reduce-scatter)
@@ -443,6 +456,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P, const 
               } else if (need_store) {
 #pragma unroll
                 for (int g = 0; g < 4; ++g) store_group(smem, fb + 8 * g, row, &v[32 * sub + 8 * g]);
+                signal_block(2 * c + sub);
               }
             } else {
               // ---- transposed chain: gradient w.r.t. the input of net layer l = 2 n_mma - m (units of sD)
@@ -491,6 +505,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P, const 
               } else if (need_store) {
 #pragma unroll
                 for (int g = 0; g < 4; ++g) store_group(smem, fb + 8 * g, row, &v[32 * sub + 8 * g]);
+                signal_block(2 * c + sub);
               }
               if (MODE == 2 && (prog_last || m == P.acc_l_prog)) {
                 // row-sum of rowscale * delta for the latent gradient; column j of this 32-block ends in lane j
@@ -502,7 +517,6 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P, const 
               }
             }
           }
-          if (need_store) signal_chunk(c);
         }
         if (fwd_last) {
           // combine the 4 partial dot products of each row (q x ch): bias, tanh (deep_sdf_decoder.py:109-110)
@@ -546,8 +560,8 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P, const 
                   x[e] = (f < LN && ((mb >> (8 * (g & 3) + e)) & 1u)) ? __ldg(P.wlast + f) * sD : 0.f;
                 }
                 store_group(smem, f0 + 8 * g, row, x);
+                if ((g & 3) == 3) signal_block(2 * c + (g >> 2));
               }
-              signal_chunk(c);
             }
           }
         }
@@ -583,6 +597,10 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P, const 
         if (io.accl && P.acc_l_prog >= 0 && f < P.accl_N && acclr[i] != 0.f) atomicAdd(io.accl + f, acclr[i] * (1.f / sD));
       }
     }
+  }
+  if (io.dbg_out && blockIdx.x == 0 && tid == 0) {
+    long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    io.dbg_out[0] = clock64() - dbg_c0; io.dbg_out[1] = t1 - dbg_t0;
   }
   tc_fence_before();
   __syncthreads();
@@ -656,11 +674,15 @@ int mlp_tc_launch(const dist_net_t* net, const NetDev& nd, int mode, const MlpAr
   P.wlast = nd.W[nl - 1]; P.blast = nd.bias[nl - 1]; P.K_last = nd.K[nl - 1];
   P.use_tanh = nd.use_tanh; P.sA = 32.0f; P.sD = 256.0f;
   P.first_append = (nd.latent_in == 1) ? 1 : 0;
+  { const char* e = getenv("DIST_TC_DEBUG"); P.dbg = e ? atoi(e) : 0; }
 
   TcIO io;
   io.points = a.points; io.n_host = a.n_host; io.n_dev = a.n_dev; io.clamp_dist = a.clamp_dist;
   io.sdf = a.sdf; io.grad = a.grad; io.coef = a.coef; io.use_clamp = a.use_clamp; io.acc0 = a.acc0; io.accl = a.accl;
   io.rows_evaluated = a.rows_evaluated;
+  io.dbg_out = nullptr;
+  static long long* dbg_buf = nullptr;
+  if (P.dbg & 4) { if (!dbg_buf) cudaMalloc(&dbg_buf, 16); io.dbg_out = dbg_buf; }
 
   // tensor map over the blob: rows of 128 B; one box = one 16 KB stage of one CTA
   CUtensorMap tmap;
@@ -690,6 +712,12 @@ int mlp_tc_launch(const dist_net_t* net, const NetDev& nd, int mode, const MlpAr
   else { mlp_tc_kernel<2><<<clusters * 2, NTHREADS, SMEM_BYTES, stream>>>(tmap, P, io); }
   count_launch();
   DIST_CHECK_CUDA(cudaGetLastError());
+  if (P.dbg & 4) {
+    long long h[2] = {0, 0};
+    cudaStreamSynchronize(stream);
+    cudaMemcpy(h, dbg_buf, 16, cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[tc dbg] mode %d: %lld cycles, %lld ns -> %.3f GHz\n", mode, h[0], h[1], h[1] ? (double)h[0] / h[1] : 0.0);
+  }
   return DIST_OK;
 }
 

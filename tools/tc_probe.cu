@@ -20,7 +20,7 @@ constexpr int KT = 32;             // K extent of the probe tile (2 MMA k-steps)
 constexpr int NPAN = KT / 8;       // K-group panels
 constexpr int A_BYTES = NPAN * 64 * 16;    // 64 rows per CTA
 constexpr int B_BYTES = NPAN * 128 * 16;   // 128 N-rows per CTA
-constexpr int OFF_A = 0, OFF_B = 4096, OFF_BAR = 16384;
+constexpr int OFF_A = 0, OFF_B = 4096, OFF_BAR = 229376;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void cluster_sync() {
@@ -59,7 +59,7 @@ __device__ __forceinline__ void commit_mc(uint32_t bar) {
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
-probe_kernel(const __grid_constant__ CUtensorMap tmapB, float* out, long long* timing, int lbo_swap, int n_chain) {
+probe_kernel(const __grid_constant__ CUtensorMap tmapB, float* out, long long* timing, int lbo_swap, int n_chain, int big_smem) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t rank = cluster_ctarank();
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -71,6 +71,7 @@ probe_kernel(const __grid_constant__ CUtensorMap tmapB, float* out, long long* t
     mbar_init(bar_full, 1);
     mbar_init(bar_done, 1);
     mbar_init(bar_done2, 1);
+    mbar_init(sbase + OFF_BAR + 24, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -155,6 +156,36 @@ probe_kernel(const __grid_constant__ CUtensorMap tmapB, float* out, long long* t
     timing[1] = t2 - t0;
   }
   if (n_chain > 0) mbar_wait(bar_done2, 0);
+  // ---- realistic pattern: A 128 KB (hi 64 KB | lo 64 KB), W ring 6 x 16 KB at 128 KB, 3 passes per k16 step
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  if (rank == 0 && tid == 0 && n_chain > 0 && big_smem) {
+    const uint32_t idesc = (1u << 4) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t bar_done3 = sbase + OFF_BAR + 24;
+    const long long t0 = clock64();
+    int it = 0, cnt = 0;
+    for (int layer = 0; layer < n_chain / 192; ++layer)
+      for (int kc = 0; kc < 16; ++kc)
+        for (int h = 0; h < 2; ++h, ++it) {
+          const uint32_t wb = sbase + 131072 + (it % 6) * 16384;
+          for (int ks = 0; ks < 2; ++ks) {
+            const uint32_t a_off = (uint32_t)(kc * 4 + ks * 2) * 1024;
+            const uint64_t a_hi = make_desc(sbase + a_off, 1024, 128), a_lo = make_desc(sbase + 65536 + a_off, 1024, 128);
+            const uint64_t b_hi = make_desc(wb + ks * 4096, 2048, 128), b_lo = make_desc(wb + 8192 + ks * 4096, 2048, 128);
+            mma_f16_2cta(tmem + h * 128, a_hi, b_hi, idesc, 1u);
+            mma_f16_2cta(tmem + h * 128, a_lo, b_hi, idesc, 1u);
+            mma_f16_2cta(tmem + h * 128, a_hi, b_lo, idesc, 1u);
+            cnt += 3;
+          }
+        }
+    commit_mc(bar_done3);
+    mbar_wait(bar_done3, 0);
+    const long long t2 = clock64();
+    timing[2] = t2 - t0;
+    timing[3] = cnt;
+  }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   cluster_sync();
@@ -185,8 +216,8 @@ int main(int argc, char** argv) {
   float* dOut;
   CK(cudaMalloc(&dOut, 2 * 128 * 256 * 4));
   long long* dT;
-  CK(cudaMalloc(&dT, 16));
-  CK(cudaMemset(dT, 0, 16));
+  CK(cudaMalloc(&dT, 64));
+  CK(cudaMemset(dT, 0, 64));
 
   EncodeFn encode = nullptr;
   cudaDriverEntryPointQueryResult qres;
@@ -201,10 +232,10 @@ int main(int argc, char** argv) {
                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) { printf("encode failed %d\n", (int)cr); return 1; }
 
-  CK(cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768));
-  for (int lbo_swap = 0; lbo_swap < 2; ++lbo_swap) {
+  CK(cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 230400));
+  for (int lbo_swap = 0; lbo_swap < 1; ++lbo_swap) {
     CK(cudaMemset(dOut, 0xFF, 2 * 128 * 256 * 4));
-    probe_kernel<<<2, 128, 32768>>>(tmap, dOut, dT, lbo_swap, lbo_swap == 0 ? n_chain : 0);
+    probe_kernel<<<2, 128, 230400>>>(tmap, dOut, dT, lbo_swap, lbo_swap == 0 ? n_chain : 0, 1);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("lbo_swap=%d: kernel failed: %s\n", lbo_swap, cudaGetErrorString(e)); return 1; }
     std::vector<float> o(2 * 128 * 256);
@@ -236,8 +267,9 @@ int main(int argc, char** argv) {
         printf("\n");
       }
     if (lbo_swap == 0) {
-      long long t[2];
-      CK(cudaMemcpy(t, dT, 16, cudaMemcpyDeviceToHost));
+      long long t[4];
+      CK(cudaMemcpy(t, dT, 32, cudaMemcpyDeviceToHost));
+      printf("realistic operand pattern (A 128 KB, W ring 96 KB, 3 passes): %lld MMAs in %lld cyc -> %.1f cyc/MMA\n", t[3], t[2], t[3] ? (double)t[2] / t[3] : 0.0);
       printf("chain of %d MMAs (M=128 pair, N=256, K=16): issue %lld cyc, complete %lld cyc -> %.1f cyc/MMA\n", n_chain, t[0], t[1],
              (double)t[1] / n_chain);
     }
