@@ -13,8 +13,8 @@
 //     256 N-rows of a stage; `.cta_group::2` copies signal the leader CTA's mbarrier), released by tcgen05.commit;
 //   * accumulators ping-pong between two 256-column TMEM buffers so the epilogue of layer l overlaps the MMAs of
 //     layer l+1 chunk by chunk (per-64-feature `a_full` barriers).
-// Warp roles per CTA (384 threads): warp 0 TMA producer, warp 1 MMA issuer (leader CTA), warp 2 TMEM allocator,
-// warps 4-11 epilogue (TMEM lane quarter = warp % 4, column half = (warp-4)/4).
+// Warp roles per CTA (640 threads): warp 0 TMA producer, warp 1 MMA issuer (leader CTA), warp 2 TMEM allocator,
+// warps 4-19 epilogue (TMEM lane quarter = warp % 4, 32-column quarter = (warp-4)/4).
 //
 // Replaces: Decoder.inference / decode_sdf (core/graph/deep_sdf_decoder.py:80-111, core/utils/decoder_utils.py:53-74)
 #include <cuda.h>
@@ -32,10 +32,10 @@ constexpr int NST = 6;                 // weight ring stages
 constexpr int STAGE_BYTES = 16384;     // per CTA: [hi 8 KB][lo 8 KB]
 constexpr int OFF_AHI = 0, OFF_ALO = 65536, OFF_W = 131072;
 constexpr int OFF_BAR = OFF_W + NST * STAGE_BYTES;   // 229376
-constexpr int OFF_PART = OFF_BAR + 256;              // per-row partial sums [64][4] (4 threads share a row)
-constexpr int OFF_ROWD = OFF_PART + 1024;            // per-row scalar [64]
-constexpr int SMEM_BYTES = OFF_ROWD + 256;           // 230912
-constexpr int NTHREADS = 384;
+constexpr int OFF_PART = OFF_BAR + 256;              // per-row partial sums [64][8] (8 threads share a row)
+constexpr int OFF_ROWD = OFF_PART + 2048;            // per-row scalar [64]
+constexpr int SMEM_BYTES = OFF_ROWD + 256;           // 231936
+constexpr int NTHREADS = 640;                        // 4 service warps + 16 epilogue warps
 constexpr int MAX_PROG = 2 * 10;                     // forward + transposed chain, at most 10 tensor-core layers each
 
 struct LayerTC {
@@ -95,14 +95,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n.reg .pred p;\nWAIT_%=:\n"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
       "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n" ::"r"(bar), "r"(parity) : "memory");
 }
 // arrive (count 1) on the barrier at the same smem offset in CTA `target_rank` of the cluster
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_local, uint32_t target_rank) {
   uint32_t remote;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(bar_local), "r"(target_rank));
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
   uint64_t d = 0;
@@ -130,7 +130,7 @@ __device__ __forceinline__ bool elect_one() {
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   uint32_t r[32];
@@ -212,7 +212,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P, const 
     for (int s = 0; s < NST; ++s) { mbar_init(W_FULL(s), 1); mbar_init(W_EMPTY(s), 1); }
     for (int c = 0; c < 16; ++c) mbar_init(A_FULL(c), 4);  // 2 warps x 2 CTAs produce each 32-feature block
     mbar_init(D_FULL(0), 1); mbar_init(D_FULL(1), 1);
-    mbar_init(FIN, 16);                                     // 8 epilogue warps x 2 CTAs
+    mbar_init(FIN, 32);                                     // 16 epilogue warps x 2 CTAs
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -272,6 +272,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P, const 
           for (int kc = 0; kc < kc32; ++kc) {
             if (!(P.dbg & 2)) mbar_wait_cluster(A_FULL(kc), (a_phase >> kc) & 1);
             a_phase ^= (1u << kc);
+            if ((P.dbg & 8) && io.dbg_out && cluster_id == 0 && t == cluster_id + n_clusters && lane == 0 && kc == 0) io.dbg_out[8 + m * 4 + 0] = clock64();
             for (int h = 0; h < nh; ++h, ++it) {
               const int slot = it % NST;
               if (!(P.dbg & 1)) mbar_wait(W_FULL(slot), (it / NST) & 1);
@@ -290,6 +291,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P, const 
                 if (kc == kc32 - 1 && h == nh - 1) commit_mc(D_FULL(buf));
               }
               __syncwarp();
+              if ((P.dbg & 8) && io.dbg_out && cluster_id == 0 && t == cluster_id + n_clusters && lane == 0 && kc == kc32 - 1 && h == nh - 1) io.dbg_out[8 + m * 4 + 1] = clock64();
             }
           }
         }
@@ -297,21 +299,22 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P, const 
       }
     }
   } else if (warp >= 4) {
-    // =============================================================== epilogue warps
+    // =============================================================== epilogue warps (16 warps, 32 rows x 32 columns each)
     const int ew = warp - 4;
     const int qq = warp & 3;             // TMEM lane quarter accessible to this warp
     const int q = qq >> 1;               // which 128-feature half of an N-half this lane quarter holds
-    const int ch = ew >> 2;              // which 64-column half of those 128 this warp handles
+    const int ch = ew >> 2;              // which 32-column quarter of those 128 this warp handles (0..3)
     const int row = 32 * (qq & 1) + lane;
     const uint32_t lane_base = (uint32_t)(32 * qq) << 16;
     const float sA = P.sA, sD = P.sD;
     const int n_mma = P.n_mma;
     float* part = reinterpret_cast<float*>(smem + OFF_PART);
     float* rowd = reinterpret_cast<float*>(smem + OFF_ROWD);
+    const int pslot = 4 * q + ch;        // this thread's slot among the 8 threads that share a row
     uint32_t G = 0, d_phase = 0;
     float px = 0.f, py = 0.f, pz = 0.f;
-    uint32_t mk[DIST_MAX_LAYERS][4];     // ReLU sign bits of this thread's (row, features) per net layer (MODE >= 1)
-    float acc0r[4] = {0.f, 0.f, 0.f, 0.f}, acclr[4] = {0.f, 0.f, 0.f, 0.f};  // MODE 2: per-lane running column sums
+    uint32_t mk[DIST_MAX_LAYERS][2];     // ReLU sign bits of this thread's (row, 32 features x 2 halves) per net layer
+    float acc0r[2] = {0.f, 0.f}, acclr[2] = {0.f, 0.f};  // MODE 2: per-lane running column sums
 
     auto load_point = [&](int64_t t) {
       const int64_t gr = t * 128 + rank * 64 + row;
@@ -323,17 +326,17 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P, const 
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(A_FULL(kc), 0);
     };
-    // layer 0 on CUDA cores: A <- split(sA * relu(b0' + W0 xyz)), features of this thread's chunks
+    // layer 0 on CUDA cores: A <- split(sA * relu(b0' + W0 xyz)) for this thread's 32-feature blocks
     auto layer0 = [&]() {
-      const int kchunks = P.L[0].kc32 >> 1;                    // 64-feature chunks the first MMA layer consumes
+      const int kblocks = P.L[0].kc32;                          // 32-feature blocks the first MMA layer consumes
       const int nh0 = (P.N0 + 255) >> 8;
       for (int h = 0; h < nh0; ++h) {
-        const int c = 4 * h + 2 * q + ch;
-        if (c >= kchunks) continue;
-        const int f0 = 64 * c;
-        uint32_t m0 = 0, m1 = 0;
-#pragma unroll 1
-        for (int g = 0; g < 8; ++g) {
+        const int kb = 8 * h + 4 * q + ch;
+        if (kb >= kblocks) continue;
+        const int f0 = 32 * kb;
+        uint32_t m0 = 0;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
           float x[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
@@ -341,17 +344,16 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P, const 
             float v = 0.f;
             if (f < P.N0) {
               v = fmaf(__ldg(P.w0 + 2 * P.N0p4 + f), pz, fmaf(__ldg(P.w0 + P.N0p4 + f), py, __ldg(P.w0 + f) * px)) + __ldg(P.bias0 + f);
-              if (v > 0.f) { if (g < 4) m0 |= 1u << (8 * g + e); else m1 |= 1u << (8 * (g - 4) + e); }
-              else v = 0.f;
+              if (v > 0.f) m0 |= 1u << (8 * g + e); else v = 0.f;
             } else if (P.first_append && f < P.N0 + 3) {
               v = (f == P.N0) ? px : ((f == P.N0 + 1) ? py : pz);
             }
             x[e] = v * sA;
           }
           store_group(smem, f0 + 8 * g, row, x);
-          if ((g & 3) == 3) signal_block(2 * c + (g >> 2));
         }
-        if (MODE != 0) { mk[0][2 * h] = m0; mk[0][2 * h + 1] = m1; }
+        if (MODE != 0) mk[0][h] = m0;
+        signal_block(kb);
       }
     };
     // sum over the 32 lanes (rows) of this warp of v[j], result for column j lands in lane j  (reduce-scatter)
@@ -368,13 +370,17 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P, const 
       }
       return v[0];
     };
+    auto row_sum8 = [&]() -> float {     // fixed-order sum of the 8 partials of this row
+      const float* pr = part + row * 8;
+      return ((pr[0] + pr[1]) + (pr[2] + pr[3])) + ((pr[4] + pr[5]) + (pr[6] + pr[7]));
+    };
 
     int64_t t = cluster_id;
     if (t < n_tiles) { load_point(t); layer0(); }
     for (; t < n_tiles; t += n_clusters) {
       const int64_t gr = t * 128 + rank * 64 + row;
       float dot = 0.f, rowscale = 0.f, dx = 0.f, dy = 0.f, dz = 0.f;
-      uint32_t mk0s[4] = {0u, 0u, 0u, 0u};
+      uint32_t mk0s[2] = {0u, 0u};
       for (int m = 0; m < n_prog; ++m, ++G) {
         const uint32_t buf = G & 1;
         const bool fwd = m < n_mma;
@@ -386,144 +392,139 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P, const 
         mbar_wait(D_FULL(buf), (d_phase >> buf) & 1);
         d_phase ^= (1u << buf);
         tc_fence_after();
+        const bool dbg_rec = (P.dbg & 8) && io.dbg_out && cluster_id == 0 && rank == 0 && warp == 4 && lane == 0 && t == cluster_id + n_clusters;
+        if (dbg_rec) io.dbg_out[8 + m * 4 + 2] = clock64();
         if (prog_last) {
           // all MMAs of this tile are complete: A is free -> start the next tile's layer 0 before draining D
-          if (MODE != 0) { mk0s[0] = mk[0][0]; mk0s[1] = mk[0][1]; mk0s[2] = mk[0][2]; mk0s[3] = mk[0][3]; }
+          if (MODE != 0) { mk0s[0] = mk[0][0]; mk0s[1] = mk[0][1]; }
           if (t + n_clusters < n_tiles) { load_point(t + n_clusters); layer0(); }
         }
-        const int kchunks_next = prog_last ? 0 : (P.L[m + 1].kc32 >> 1);
+        const int kblocks_next = prog_last ? 0 : P.L[m + 1].kc32;
         // net layer whose ReLU mask gates the values produced here (transposed chain): l-1 with l = 2 n_mma - m
         const int mask_layer = fwd ? (m + 1) : (2 * n_mma - m - 1);
         for (int h = 0; h < Lnh; ++h) {
-          const int c = 4 * h + 2 * q + ch;
-          const int f0 = 256 * h + 128 * q + 64 * ch;
+          const int kb = 8 * h + 4 * q + ch;             // 32-feature block index == K block of the next layer
+          const int fb = 32 * kb;
           bool need_store = false, process = false;
-          if (fwd && !fwd_last) { need_store = c < kchunks_next; process = need_store; }
-          else if (fwd_last) { process = f0 < LN; }
-          else if (!prog_last) { need_store = c < kchunks_next; process = need_store || (Lapp && f0 < LN + 3 && f0 + 64 > LN); }
-          else { process = f0 < LN + 3 * Lapp; }
+          if (fwd && !fwd_last) { need_store = kb < kblocks_next; process = need_store; }
+          else if (fwd_last) { process = fb < LN; }
+          else if (!prog_last) { need_store = kb < kblocks_next; process = need_store || (Lapp && fb < LN + 3 && fb + 32 > LN); }
+          else { process = fb < LN + 3 * Lapp; }
           if (!process) continue;
-          float v[64];
-          tmem_ld64(tmem + lane_base + buf * 256 + h * 128 + 64 * ch, v);
+          float v[32];
+          tmem_ld32(tmem + lane_base + buf * 256 + h * 128 + 32 * ch, v);
+          const bool interior = (fb + 32 <= LN);            // warp-uniform: no per-element bounds checks
+          if (fwd) {
+            // ---- forward: bias + ReLU (deep_sdf_decoder.py:96,105); values are carried in units of sA
+            uint32_t mb = 0;
+            if (interior) {
 #pragma unroll
-          for (int sub = 0; sub < 2; ++sub) {
-            const int fb = f0 + 32 * sub;
-            const bool interior = (fb + 32 <= LN);            // warp-uniform: no per-element bounds checks
-            if (fwd) {
-              // ---- forward: bias + ReLU (deep_sdf_decoder.py:96,105); values are carried in units of sA
-              uint32_t mb = 0;
+              for (int j4 = 0; j4 < 8; ++j4) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(Lbias + fb) + j4);
+                const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const int j = 4 * j4 + e;
+                  const float a = fmaf(v[j], cscale, bb[e]);
+                  if (MODE != 0) mb |= (a > 0.f) ? (1u << j) : 0u;
+                  v[j] = fmaxf(a, 0.f);
+                }
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const int f = fb + j;
+                float a = 0.f;
+                if (f < LN) {
+                  a = fmaf(v[j], cscale, __ldg(Lbias + f));
+                  if (a > 0.f) mb |= 1u << j; else a = 0.f;
+                } else if (Lapp && f < LN + 3) {
+                  a = ((f == LN) ? px : ((f == LN + 1) ? py : pz)) * sA;
+                }
+                v[j] = a;
+              }
+            }
+            if (MODE != 0) mk[m + 1][h] = mb;
+            if (fwd_last) {
               if (interior) {
 #pragma unroll
                 for (int j4 = 0; j4 < 8; ++j4) {
-                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(Lbias + fb) + j4);
-                  const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) {
-                    const int j = 32 * sub + 4 * j4 + e;
-                    const float a = fmaf(v[j], cscale, bb[e]);
-                    if (MODE != 0) mb |= (a > 0.f) ? (1u << (4 * j4 + e)) : 0u;
-                    v[j] = fmaxf(a, 0.f);
-                  }
+                  const float4 w4 = __ldg(reinterpret_cast<const float4*>(P.wlast + fb) + j4);
+                  dot = fmaf(v[4 * j4], w4.x, dot); dot = fmaf(v[4 * j4 + 1], w4.y, dot);
+                  dot = fmaf(v[4 * j4 + 2], w4.z, dot); dot = fmaf(v[4 * j4 + 3], w4.w, dot);
                 }
               } else {
 #pragma unroll
-                for (int jj = 0; jj < 32; ++jj) {
-                  const int j = 32 * sub + jj, f = fb + jj;
-                  float a = 0.f;
-                  if (f < LN) {
-                    a = fmaf(v[j], cscale, __ldg(Lbias + f));
-                    if (a > 0.f) mb |= 1u << jj; else a = 0.f;
-                  } else if (Lapp && f < LN + 3) {
-                    a = ((f == LN) ? px : ((f == LN + 1) ? py : pz)) * sA;
-                  }
-                  v[j] = a;
-                }
+                for (int j = 0; j < 32; ++j)
+                  if (fb + j < LN) dot = fmaf(v[j], __ldg(P.wlast + fb + j), dot);
               }
-              if (MODE != 0) mk[m + 1][2 * h + sub] = mb;
-              if (fwd_last) {
-                if (interior) {
+            } else if (need_store) {
 #pragma unroll
-                  for (int j4 = 0; j4 < 8; ++j4) {
-                    const float4 w4 = __ldg(reinterpret_cast<const float4*>(P.wlast + fb) + j4);
-                    dot = fmaf(v[32 * sub + 4 * j4], w4.x, dot); dot = fmaf(v[32 * sub + 4 * j4 + 1], w4.y, dot);
-                    dot = fmaf(v[32 * sub + 4 * j4 + 2], w4.z, dot); dot = fmaf(v[32 * sub + 4 * j4 + 3], w4.w, dot);
-                  }
-                } else {
+              for (int g = 0; g < 4; ++g) store_group(smem, fb + 8 * g, row, &v[8 * g]);
+              signal_block(kb);
+            }
+          } else {
+            // ---- transposed chain: gradient w.r.t. the input of net layer l = 2 n_mma - m (units of sD)
+            const uint32_t mb = (mask_layer == 0 && prog_last) ? mk0s[h] : mk[mask_layer][h];
+            if (interior) {
 #pragma unroll
-                  for (int jj = 0; jj < 32; ++jj)
-                    if (fb + jj < LN) dot = fmaf(v[32 * sub + jj], __ldg(P.wlast + fb + jj), dot);
-                }
-              } else if (need_store) {
-#pragma unroll
-                for (int g = 0; g < 4; ++g) store_group(smem, fb + 8 * g, row, &v[32 * sub + 8 * g]);
-                signal_block(2 * c + sub);
-              }
+              for (int j = 0; j < 32; ++j) v[j] = ((mb >> j) & 1u) ? v[j] * cscale : 0.f;
             } else {
-              // ---- transposed chain: gradient w.r.t. the input of net layer l = 2 n_mma - m (units of sD)
-              const uint32_t mb = (mask_layer == 0 && prog_last) ? mk0s[2 * h + sub] : mk[mask_layer][2 * h + sub];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const int f = fb + j;
+                const float g = v[j] * cscale;
+                float d = 0.f;
+                if (f < LN) d = ((mb >> j) & 1u) ? g : 0.f;
+                else if (Lapp && f < LN + 3) { if (f == LN) dx += g; else if (f == LN + 1) dy += g; else dz += g; }
+                v[j] = d;
+              }
+            }
+            if (prog_last) {
+              // delta of layer 0's pre-activation: chain to xyz through W0 (K = 3, CUDA cores)
               if (interior) {
 #pragma unroll
-                for (int jj = 0; jj < 32; ++jj) {
-                  const int j = 32 * sub + jj;
-                  v[j] = ((mb >> jj) & 1u) ? v[j] * cscale : 0.f;
+                for (int j4 = 0; j4 < 8; ++j4) {
+                  const float4 wx = __ldg(reinterpret_cast<const float4*>(P.w0 + fb) + j4);
+                  const float4 wy = __ldg(reinterpret_cast<const float4*>(P.w0 + P.N0p4 + fb) + j4);
+                  const float4 wz = __ldg(reinterpret_cast<const float4*>(P.w0 + 2 * P.N0p4 + fb) + j4);
+                  const int j = 4 * j4;
+                  dx = fmaf(v[j], wx.x, dx); dx = fmaf(v[j + 1], wx.y, dx); dx = fmaf(v[j + 2], wx.z, dx); dx = fmaf(v[j + 3], wx.w, dx);
+                  dy = fmaf(v[j], wy.x, dy); dy = fmaf(v[j + 1], wy.y, dy); dy = fmaf(v[j + 2], wy.z, dy); dy = fmaf(v[j + 3], wy.w, dy);
+                  dz = fmaf(v[j], wz.x, dz); dz = fmaf(v[j + 1], wz.y, dz); dz = fmaf(v[j + 2], wz.z, dz); dz = fmaf(v[j + 3], wz.w, dz);
                 }
               } else {
 #pragma unroll
-                for (int jj = 0; jj < 32; ++jj) {
-                  const int j = 32 * sub + jj, f = fb + jj;
-                  const float g = v[j] * cscale;
-                  float d = 0.f;
-                  if (f < LN) d = ((mb >> jj) & 1u) ? g : 0.f;
-                  else if (Lapp && f < LN + 3) { if (f == LN) dx += g; else if (f == LN + 1) dy += g; else dz += g; }
-                  v[j] = d;
-                }
-              }
-              if (prog_last) {
-                // delta of layer 0's pre-activation: chain to xyz through W0 (K = 3, CUDA cores)
-                if (interior) {
-#pragma unroll
-                  for (int j4 = 0; j4 < 8; ++j4) {
-                    const float4 wx = __ldg(reinterpret_cast<const float4*>(P.w0 + fb) + j4);
-                    const float4 wy = __ldg(reinterpret_cast<const float4*>(P.w0 + P.N0p4 + fb) + j4);
-                    const float4 wz = __ldg(reinterpret_cast<const float4*>(P.w0 + 2 * P.N0p4 + fb) + j4);
-                    const int j = 32 * sub + 4 * j4;
-                    dx = fmaf(v[j], wx.x, dx); dx = fmaf(v[j + 1], wx.y, dx); dx = fmaf(v[j + 2], wx.z, dx); dx = fmaf(v[j + 3], wx.w, dx);
-                    dy = fmaf(v[j], wy.x, dy); dy = fmaf(v[j + 1], wy.y, dy); dy = fmaf(v[j + 2], wy.z, dy); dy = fmaf(v[j + 3], wy.w, dy);
-                    dz = fmaf(v[j], wz.x, dz); dz = fmaf(v[j + 1], wz.y, dz); dz = fmaf(v[j + 2], wz.z, dz); dz = fmaf(v[j + 3], wz.w, dz);
-                  }
-                } else {
-#pragma unroll
-                  for (int jj = 0; jj < 32; ++jj) {
-                    const int f = fb + jj;
-                    if (f < LN) {
-                      dx = fmaf(v[32 * sub + jj], __ldg(P.w0 + f), dx);
-                      dy = fmaf(v[32 * sub + jj], __ldg(P.w0 + P.N0p4 + f), dy);
-                      dz = fmaf(v[32 * sub + jj], __ldg(P.w0 + 2 * P.N0p4 + f), dz);
-                    }
+                for (int j = 0; j < 32; ++j) {
+                  const int f = fb + j;
+                  if (f < LN) {
+                    dx = fmaf(v[j], __ldg(P.w0 + f), dx);
+                    dy = fmaf(v[j], __ldg(P.w0 + P.N0p4 + f), dy);
+                    dz = fmaf(v[j], __ldg(P.w0 + 2 * P.N0p4 + f), dz);
                   }
                 }
-              } else if (need_store) {
-#pragma unroll
-                for (int g = 0; g < 4; ++g) store_group(smem, fb + 8 * g, row, &v[32 * sub + 8 * g]);
-                signal_block(2 * c + sub);
               }
-              if (MODE == 2 && (prog_last || m == P.acc_l_prog)) {
-                // row-sum of rowscale * delta for the latent gradient; column j of this 32-block ends in lane j
-                float w32[32];
+            } else if (need_store) {
 #pragma unroll
-                for (int jj = 0; jj < 32; ++jj) w32[jj] = v[32 * sub + jj] * rowscale;
-                const float sres = colsum32(w32);
-                if (prog_last) acc0r[2 * h + sub] += sres; else acclr[2 * h + sub] += sres;
-              }
+              for (int g = 0; g < 4; ++g) store_group(smem, fb + 8 * g, row, &v[8 * g]);
+              signal_block(kb);
+            }
+            if (MODE == 2 && (prog_last || m == P.acc_l_prog)) {
+              // row-sum of rowscale * delta for the latent gradient; column j of this 32-block ends in lane j
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] *= rowscale;
+              const float sres = colsum32(v);
+              if (prog_last) acc0r[h] += sres; else acclr[h] += sres;
             }
           }
         }
+        if (dbg_rec) io.dbg_out[8 + m * 4 + 3] = clock64();
         if (fwd_last) {
-          // combine the 4 partial dot products of each row (q x ch): bias, tanh (deep_sdf_decoder.py:109-110)
-          part[row * 4 + 2 * q + ch] = dot;
+          // combine the 8 partial dot products of each row: bias, tanh (deep_sdf_decoder.py:109-110)
+          part[row * 8 + pslot] = dot;
           epi_bar_sync();
-          if (q == 0 && ch == 0) {
-            const float s = ((part[row * 4] + part[row * 4 + 1]) + (part[row * 4 + 2] + part[row * 4 + 3])) * (1.f / sA) + __ldg(P.blast);
+          if (pslot == 0) {
+            const float s = row_sum8() * (1.f / sA) + __ldg(P.blast);
             float t1 = s, o = tanhf(s);
             if (P.use_tanh) { t1 = o; o = tanhf(o); }
             float oc = o;
@@ -545,23 +546,23 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P, const 
           if (MODE != 0) {
             rowscale = rowd[row];
             // seed of the transposed chain (unit): delta[f] = w_last[f] * relu'(f), as A of the first transposed layer
-            const int kchunks = P.L[n_mma].kc32 >> 1;
+            const int kblocks = P.L[n_mma].kc32;
             for (int h = 0; h < Lnh; ++h) {
-              const int c = 4 * h + 2 * q + ch;
-              if (c >= kchunks) continue;
-              const int f0 = 64 * c;
-#pragma unroll 1
-              for (int g = 0; g < 8; ++g) {
+              const int kb = 8 * h + 4 * q + ch;
+              if (kb >= kblocks) continue;
+              const int f0 = 32 * kb;
+              const uint32_t mb = mk[n_mma][h];
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
                 float x[8];
-                const uint32_t mb = mk[n_mma][2 * h + (g >> 2)];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                   const int f = f0 + 8 * g + e;
-                  x[e] = (f < LN && ((mb >> (8 * (g & 3) + e)) & 1u)) ? __ldg(P.wlast + f) * sD : 0.f;
+                  x[e] = (f < LN && ((mb >> (8 * g + e)) & 1u)) ? __ldg(P.wlast + f) * sD : 0.f;
                 }
                 store_group(smem, f0 + 8 * g, row, x);
-                if ((g & 3) == 3) signal_block(2 * c + (g >> 2));
               }
+              signal_block(kb);
             }
           }
         }
@@ -571,16 +572,16 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P, const 
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(FIN, 0);
           if (MODE != 0) {
-            // combine the 4 partial d/dxyz of each row, scale by the row's upstream factor, write out
+            // combine the 8 partial d/dxyz of each row, scale by the row's upstream factor, write out
             float res[3];
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-              part[row * 4 + 2 * q + ch] = (k == 0) ? dx : ((k == 1) ? dy : dz);
+              part[row * 8 + pslot] = (k == 0) ? dx : ((k == 1) ? dy : dz);
               epi_bar_sync();
-              res[k] = (part[row * 4] + part[row * 4 + 1]) + (part[row * 4 + 2] + part[row * 4 + 3]);
+              res[k] = row_sum8();
               epi_bar_sync();
             }
-            if (q == 0 && ch == 0 && gr < n && io.grad) {
+            if (pslot == 0 && gr < n && io.grad) {
               const float rs = rowscale * (1.f / sD);
               io.grad[gr * 3] = res[0] * rs; io.grad[gr * 3 + 1] = res[1] * rs; io.grad[gr * 3 + 2] = res[2] * rs;
             }
@@ -589,12 +590,12 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P, const 
       }
     }
     if (MODE == 2) {
-      // flush the per-lane running column sums: lane j of this warp holds columns f0 + 32 sub + j of its chunks
+      // flush the per-lane running column sums: lane j of this warp holds column 32*kb + j of its blocks
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int f = 256 * (i >> 1) + 128 * q + 64 * ch + 32 * (i & 1) + lane;
-        if (io.acc0 && f < P.N0 && acc0r[i] != 0.f) atomicAdd(io.acc0 + f, acc0r[i] * (1.f / sD));
-        if (io.accl && P.acc_l_prog >= 0 && f < P.accl_N && acclr[i] != 0.f) atomicAdd(io.accl + f, acclr[i] * (1.f / sD));
+      for (int h = 0; h < 2; ++h) {
+        const int f = 32 * (8 * h + 4 * q + ch) + lane;
+        if (io.acc0 && f < P.N0 && acc0r[h] != 0.f) atomicAdd(io.acc0 + f, acc0r[h] * (1.f / sD));
+        if (io.accl && P.acc_l_prog >= 0 && f < P.accl_N && acclr[h] != 0.f) atomicAdd(io.accl + f, acclr[h] * (1.f / sD));
       }
     }
   }
@@ -682,7 +683,7 @@ int mlp_tc_launch(const dist_net_t* net, const NetDev& nd, int mode, const MlpAr
   io.rows_evaluated = a.rows_evaluated;
   io.dbg_out = nullptr;
   static long long* dbg_buf = nullptr;
-  if (P.dbg & 4) { if (!dbg_buf) cudaMalloc(&dbg_buf, 16); io.dbg_out = dbg_buf; }
+  if (P.dbg & 4) { if (!dbg_buf) { cudaMalloc(&dbg_buf, 2048); cudaMemset(dbg_buf, 0, 2048); } io.dbg_out = dbg_buf; }
 
   // tensor map over the blob: rows of 128 B; one box = one 16 KB stage of one CTA
   CUtensorMap tmap;
@@ -717,6 +718,14 @@ int mlp_tc_launch(const dist_net_t* net, const NetDev& nd, int mode, const MlpAr
     cudaStreamSynchronize(stream);
     cudaMemcpy(h, dbg_buf, 16, cudaMemcpyDeviceToHost);
     fprintf(stderr, "[tc dbg] mode %d: %lld cycles, %lld ns -> %.3f GHz\n", mode, h[0], h[1], h[1] ? (double)h[0] / h[1] : 0.0);
+    if (P.dbg & 8) {
+      long long ev[256];
+      cudaMemcpy(ev, dbg_buf, 2048, cudaMemcpyDeviceToHost);
+      const long long t0 = ev[8];
+      for (int m = 0; m < P.n_prog; ++m)
+        fprintf(stderr, "[tc dbg] layer %2d: mma start %7lld  issue end %7lld | epi start %7lld  epi end %7lld\n", m, ev[8 + m * 4] - t0,
+                ev[8 + m * 4 + 1] - t0, ev[8 + m * 4 + 2] - t0, ev[8 + m * 4 + 3] - t0);
+    }
   }
   return DIST_OK;
 }
