@@ -17,14 +17,13 @@ image has round(512*sqrt(N))^2 pixels (same view, finer sampling), rows interlea
             (F = 3,146,752 flop per folded row) against the measured dense bf16 peak of MEASURED_PEAKS.json.
 """
 import argparse
+import gc
 import importlib
 import json
 import math
 import os
 import statistics
-import subprocess
 import sys
-import tempfile
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -51,52 +50,63 @@ def loss_of(out):
 
 
 class ClockSampler(object):
-    """nvidia-smi sampling of SM clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """NVML sampling (background thread, 20 ms period) of SM clocks, power and throttle reasons during the timed
+    region.  NVML in-process instead of an `nvidia-smi -lms` subprocess: the subprocess costs ~100 ms per sample and
+    measurably slows a 50-80 ms step."""
 
     def __init__(self, index):
-        self.index, self.f, self.p = index, None, None
+        self.index, self.rows, self.stop, self.th, self.h, self.nv = index, [], False, None, None, None
 
     def __enter__(self):
         try:
-            self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
-                                      stderr=subprocess.DEVNULL)
+            if self.index < 0:
+                raise RuntimeError('sampler disabled')
+            import threading
+            import pynvml as nv
+            nv.nvmlInit()
+            self.nv = nv
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].isdigit() else self.index
+            self.h = nv.nvmlDeviceGetHandleByIndex(phys)
+            self.max_sm = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+
+            def run():
+                while not self.stop:
+                    try:
+                        self.rows.append((nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM),
+                                          nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0,
+                                          nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)))
+                    except Exception:
+                        pass
+                    time.sleep(0.02)
+            self.th = threading.Thread(target=run, daemon=True)
+            self.th.start()
         except Exception:
-            self.p = None
+            self.th = None
         return self
 
     def __exit__(self, *a):
-        if self.p is not None:
-            self.p.terminate()
-            try:
-                self.p.wait(timeout=5)
-            except Exception:
-                self.p.kill()
+        self.stop = True
+        if self.th is not None:
+            self.th.join(timeout=2)
 
     def summary(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        if self.f is None:
+        if not self.rows:
             return out
-        try:
-            self.f.flush()
-            rows = [l.split(",") for l in open(self.f.name).read().strip().splitlines() if l.count(",") >= 8]
-            sm = [float(r[1]) for r in rows]
-            if sm:
-                out["sm_mhz"] = statistics.median(sm)
-                out["sm_max_mhz"] = float(rows[0][2])
-                out["power_w_max"] = max(float(r[3]) for r in rows)
-                names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-                for i, n in enumerate(names):
-                    if any("Active" in r[5 + i] and "Not" not in r[5 + i] for r in rows):
-                        out["reasons"].append(n)
-                out["samples"] = len(rows)
-            os.unlink(self.f.name)
-        except Exception:
-            pass
+        nv = self.nv
+        out["sm_mhz"] = statistics.median(r[0] for r in self.rows)
+        out["sm_max_mhz"] = self.max_sm
+        out["power_w_max"] = max(r[1] for r in self.rows)
+        out["samples"] = len(self.rows)
+        bits = 0
+        for r in self.rows:
+            bits |= r[2]
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        out["reasons"] = [k for k, v in names.items() if bits & v]
         return out
 
 
@@ -251,16 +261,23 @@ def main():
     if world > 1:
         dist.barrier()
     ren.local.reset_row_counter()
+    gc.collect()
+    gc.disable()   # no cyclic-GC pauses inside the timed regions (re-enabled below)
     l0 = lib.dist_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clk:
+    with ClockSampler(local_rank if not os.environ.get('BENCH_NO_SAMPLER') else -1) as clk:
         torch.cuda.synchronize()
         e0.record()
+        marks = []
         for _ in range(args.steps):
             full, g = step_device(lat_d, R_d, T_d)
             flush.fill_(1.0)
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            marks.append(ev)
         e1.record()
         torch.cuda.synchronize()
+    step_ms = [round((e0 if i == 0 else marks[i - 1]).elapsed_time(marks[i]), 2) for i in range(len(marks))]
     launches = lib.dist_launch_count() - l0
     ms = e0.elapsed_time(e1)
     rows_f, rows_g = int(ren.local.rows_evaluated.item()), int(ren.local.rows_grad.item())
@@ -306,6 +323,7 @@ def main():
         dist.barrier()
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_e = float(t.item())
+    gc.enable()
     e2e_value = side * side * args.steps / (ms_e * 1e-3)
     h2d = (lat_p.numel() + R_p.numel() + T_p.numel()) * 4
     d2h = sum(o.numel() * o.element_size() for o in outs_p) + g_p.numel() * 4
@@ -349,7 +367,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e / args.steps},
             "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu_baseline,
-            "engine": "tc" if ren.local.plan.tc is not None else "simt",
+            "engine": "tc" if ren.local.plan.tc is not None else "simt", "step_ms": step_ms,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -70,10 +70,12 @@ class _RenderDepthFn(torch.autograd.Function):
         ctx.save_for_backward(latent, Rd, T.detach().float())
         hit = saved["flags"].bitwise_and(1).bool()
         ctx.mark_non_differentiable(mask, hit)
-        return Zdepth, mask, min_sdf, hit, saved["dist"]
+        # NB: nothing stored on ctx may also be returned (tensor -> grad_fn -> ctx -> tensor would be a reference cycle
+        # that only the cyclic GC frees, i.e. ~60 MB of saved samples per render lingering for many steps)
+        return Zdepth, mask, min_sdf, hit
 
     @staticmethod
-    def backward(ctx, gZ, _gmask, gM, _ghit, _gdist):
+    def backward(ctx, gZ, _gmask, gM, _ghit):
         latent, Rd, Td = ctx.saved_tensors
         ren, opts, lib, st = ctx.ren, ctx.opts, _abi.lib(), _stream()
         plan, dev, P, B = ren.plan, ren.device, ren.P, ren.buffer_size
@@ -95,12 +97,7 @@ class _RenderDepthFn(torch.autograd.Function):
         d_ray = torch.zeros(3, P, **f32) if want_cam else None
         g_lat = g_R = g_T = None
         if gZ is not None or gM is not None:
-            rows = P * B
-            s_row = torch.empty(rows, device=dev, dtype=torch.int32)
-            s_pts = torch.empty(rows, 3, **f32)
-            s_coef = torch.empty(rows, **f32)
-            s_dpts = torch.empty(rows, 3, **f32)
-            s_cnt = torch.empty(1, device=dev, dtype=torch.int32)
+            s_row, s_pts, s_coef, s_dpts, s_cnt = scr["b_row"], scr["b_pts"], scr["b_coef"], scr["b_dpts"], scr["b_cnt"]
             _abi.check(lib.dist_render_depth_bwd(net, ctx.engine, cam, ctx.mp, ws, _abi.ptr(gZ), _abi.ptr(gM),
                                                  _abi.ptr(acc0), _abi.ptr(accl), _abi.ptr(d_cam), _abi.ptr(d_ray),
                                                  _abi.ptr(s_row), _abi.ptr(s_pts), _abi.ptr(s_coef), None,
@@ -261,8 +258,17 @@ class SDFRenderer(object):
                 "counts": torch.empty(self.march_step + 2, **i32),
                 "n_idx": torch.empty(P, **i32), "n_pts": torch.empty(P, 3, **f32), "n_grad": torch.empty(P, 3, **f32),
                 "n_cnt": torch.empty(1, **i32),
+                # backward replay rows (at most P * buffer_size)
+                "b_row": torch.empty(P * self.buffer_size, **i32), "b_pts": torch.empty(P * self.buffer_size, 3, **f32),
+                "b_coef": torch.empty(P * self.buffer_size, **f32), "b_dpts": torch.empty(P * self.buffer_size, 3, **f32),
+                "b_cnt": torch.empty(1, **i32),
             }
         return self._scr
+
+    def _raise_if_empty(self):
+        """renderer.py:214-215.  Reads one int back from the device, i.e. waits for the enqueued march."""
+        if int(self._last_counts[0].item()) == 0:
+            raise ValueError('No valid depth.')
 
     def reset_row_counter(self):
         self.rows_evaluated.zero_()
@@ -290,9 +296,9 @@ class SDFRenderer(object):
         opts = dict(kind=ray_marching_type, clamp_dist=clamp_dist, use_transform=use_transform, engine=self.engine,
                     want_depth_grad=any_grad and not no_grad_depth, want_mask_grad=any_grad and not no_grad_mask,
                     want_camera_grad=any_grad and not no_grad_camera, replay=not no_grad_depth)
-        Zdepth, mask, min_sdf, hit, dist = _RenderDepthFn.apply(latent, R, T, self, opts)
-        if check_empty and int(self._last_counts[0].item()) == 0:
-            raise ValueError('No valid depth.')  # renderer.py:214-215
+        Zdepth, mask, min_sdf, hit = _RenderDepthFn.apply(latent, R, T, self, opts)
+        if check_empty:
+            self._raise_if_empty()
         if torch.is_grad_enabled() and (R.requires_grad or T.requires_grad):
             # renderer.py:842,863: the fill of rays missing the unit sphere stays differentiable w.r.t. the camera
             cam_pos = self.get_camera_location(R, T)
@@ -343,14 +349,16 @@ class SDFRenderer(object):
         Zdepth, valid_mask, min_abs_query = self.render_depth(
             latent, R, T, clamp_dist=clamp_dist, sample_index_type=sample_index_type, profile=profile, no_grad=no_grad,
             no_grad_depth=no_grad_depth, no_grad_mask=no_grad_mask, no_grad_camera=no_grad_camera,
-            ray_marching_type=ray_marching_type, use_transform=use_transform)
+            ray_marching_type=ray_marching_type, use_transform=use_transform, check_empty=False)
         depth = torch.where(valid_mask, Zdepth * self.calib_map, torch.full_like(Zdepth, 1e11))  # renderer.py:967-969
         normal = self.render_normal(latent, R, T, Zdepth, valid_mask, clamp_dist=clamp_dist, no_grad=no_grad_normal,
                                     normalize=normalize_normal, use_transform=use_transform)
         normal = torch.matmul(R if not no_grad_normal else R.detach(), normal)  # renderer.py:978
         normal = torch.cat([normal[:1] * (-1), normal[1:]], 0)                   # renderer.py:979
         normal = normal.reshape(3, h, w).permute(1, 2, 0)
-        return depth.reshape(h, w), normal, valid_mask.reshape(h, w).type(torch.uint8), min_abs_query.reshape(h, w)
+        out = (depth.reshape(h, w), normal, valid_mask.reshape(h, w).type(torch.uint8), min_abs_query.reshape(h, w))
+        self._raise_if_empty()   # deferred to here so that the whole render is enqueued before the host waits
+        return out
 
     def render_silhouette(self, latent, R, T, **kw):
         """(mask[h,w] uint8, min_abs_query[h,w]): the pair the reference uses as the silhouette (renderer.py:878,990)."""
