@@ -67,6 +67,7 @@ def gather_bands(outs, img_hw, rank, world, extra=None, group=None):
     if world == 1:
         gathered = flat[None]
     else:
-        gathered = torch.empty(world, flat.numel(), device=flat.device, dtype=torch.float32)
-        dist.all_gather_into_tensor(gathered, flat, group=group)
+        gathered = torch.empty(world * flat.numel(), device=flat.device, dtype=torch.float32)
+        dist.all_gather_into_tensor(gathered, flat, group=group)      # flat output: accepted by NCCL and gloo alike
+        gathered = gathered.view(world, flat.numel())
     return unpack_bands(gathered, img_hw, world, 0 if extra is None else extra.numel())
