@@ -13,7 +13,7 @@ MAX_LAYERS = 16
 MAX_WIDTH = 512
 MAX_BUFFER = 8
 ENGINE_SIMT, ENGINE_TC = 0, 1
-MARCH_TRIVIAL, MARCH_RECURSIVE = 0, 1
+MARCH_TRIVIAL, MARCH_RECURSIVE, MARCH_PYRAMID = 0, 1, 2
 
 c_f32p = C.POINTER(C.c_float)
 
@@ -40,11 +40,11 @@ class Camera(C.Structure):
 class March(C.Structure):
     _fields_ = [("march_step", C.c_int32), ("buffer_size", C.c_int32), ("marching_type", C.c_int32),
                 ("first_query_check", C.c_int32), ("ratio", C.c_float), ("threshold", C.c_float),
-                ("clamp_dist", C.c_float), ("replay_grad_rounding", C.c_int32)]
+                ("clamp_dist", C.c_float), ("replay_grad_rounding", C.c_int32), ("coarse_steps", C.c_int32 * 2)]
 
 
 WS_FIELDS = ["ray", "entry", "exit_", "dist", "z", "flags", "nreal", "top_sdf", "top_pt", "top_zafter", "top_zgen",
-             "list_a", "list_b", "pts", "sdf", "counts", "sdf_origin"]
+             "list_a", "list_b", "pts", "sdf", "counts", "sdf_origin", "entry0", "top_lvl", "pyr_f", "pyr_i", "pyr_b"]
 
 
 class Workspace(C.Structure):
@@ -71,7 +71,7 @@ PROTOTYPES = {
                                          C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_void_p, C.c_void_p]),
     "dist_render_depth_bwd": (C.c_int, [C.POINTER(Net), C.c_int, C.POINTER(Camera), C.POINTER(March),
-                                        C.POINTER(Workspace)] + [C.c_void_p] * 14),
+                                        C.POINTER(Workspace)] + [C.c_void_p] * 15),
 }
 
 _lib = None

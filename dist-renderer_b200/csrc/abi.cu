@@ -69,7 +69,7 @@ int render_depth_fwd(const dist_net_t*, int, const dist_camera_t*, const dist_ma
 int render_normal_fwd(const dist_net_t*, int, const dist_camera_t*, const float*, const uint8_t*, float, int, float*,
                       int32_t*, float*, float*, int32_t*, int64_t*, cudaStream_t);
 int render_depth_bwd(const dist_net_t*, int, const dist_camera_t*, const dist_march_t*, const dist_workspace_t*,
-                     const float*, const float*, float*, float*, float*, float*, int32_t*, float*, float*, uint8_t*,
+                     const float*, const float*, float*, float*, float*, float*, float*, int32_t*, float*, float*, uint8_t*,
                      float*, int32_t*, int64_t*, cudaStream_t);
 
 }  // namespace dist
@@ -161,12 +161,12 @@ int dist_render_normal_fwd(const dist_net_t* net, int engine, const dist_camera_
 
 int dist_render_depth_bwd(const dist_net_t* net, int engine, const dist_camera_t* cam, const dist_march_t* mp,
                           const dist_workspace_t* ws, const float* gZ, const float* gM, float* acc0, float* accl,
-                          float* d_cam_pos, float* d_ray, int32_t* scratch_row_pix, float* scratch_pts,
+                          float* d_cam_pos, float* d_ray, float* d_ray_coarse, int32_t* scratch_row_pix, float* scratch_pts,
                           float* scratch_coef, uint8_t* scratch_clamp, float* scratch_dpts, int32_t* scratch_count,
                           int64_t* rows_evaluated, void* stream) {
   DIST_REQUIRE(net && cam && mp && ws && acc0 && scratch_row_pix && scratch_pts && scratch_coef && scratch_dpts &&
                    scratch_count, "render_depth_bwd: null argument");
-  return render_depth_bwd(net, engine, cam, mp, ws, gZ, gM, acc0, accl, d_cam_pos, d_ray, scratch_row_pix, scratch_pts,
+  return render_depth_bwd(net, engine, cam, mp, ws, gZ, gM, acc0, accl, d_cam_pos, d_ray, d_ray_coarse, scratch_row_pix, scratch_pts,
                           scratch_coef, scratch_clamp, scratch_dpts, scratch_count, rows_evaluated,
                           (cudaStream_t)stream);
 }

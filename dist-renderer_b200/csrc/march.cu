@@ -9,6 +9,7 @@
 // selection and depth estimate), :836-910 (render_depth / render_normal).
 #include <cuda_runtime.h>
 #include <math.h>
+#include <string.h>
 #include "common.cuh"
 
 namespace dist {
@@ -33,10 +34,8 @@ __device__ __forceinline__ int warp_append(int32_t* counter, bool pred) {
   return pred ? base + __popc(m & ((1u << lane) - 1)) : -1;
 }
 
-// unit ray through local pixel lp, world frame (renderer.py:39,190-200)
-__device__ __forceinline__ void pixel_ray(const Cam& cam, const float* R, int lp, float (&ray)[3]) {
-  const float x = (float)(lp % cam.W);
-  const float y = (float)(cam.row0 + (lp / cam.W) * cam.row_step);
+// unit ray through pixel coordinates (x, y), world frame (renderer.py:39,190-200; :631-636 for pyramid levels)
+__device__ __forceinline__ void coord_ray(const Cam& cam, const float* R, float x, float y, float (&ray)[3]) {
   float hc[3], v[3];
 #pragma unroll
   for (int i = 0; i < 3; ++i) hc[i] = fmaf(cam.Kinv[i * 3 + 2], 1.f, fmaf(cam.Kinv[i * 3 + 1], y, cam.Kinv[i * 3] * x));
@@ -46,6 +45,58 @@ __device__ __forceinline__ void pixel_ray(const Cam& cam, const float* R, int lp
 #pragma unroll
   for (int i = 0; i < 3; ++i) ray[i] = v[i] / nrm;
 }
+__device__ __forceinline__ void pixel_ray(const Cam& cam, const float* R, int lp, float (&ray)[3]) {
+  coord_ray(cam, R, (float)(lp % cam.W), (float)(cam.row0 + (lp / cam.W) * cam.row_step), ray);
+}
+
+// unit-sphere geometry of one ray (renderer.py:225-282): distance to the origin, hit flag, entry and exit depth
+__device__ __forceinline__ void sphere_geom(const float (&c)[3], const float (&ray)[3], float radius, float& dist, bool& hit,
+                                            float& entry, float& ex) {
+  const float ptq = (c[0] * ray[0] + c[1] * ray[1]) + c[2] * ray[2];
+  const float d0 = c[0] - ptq * ray[0], d1 = c[1] - ptq * ray[1], d2 = c[2] - ptq * ray[2];
+  dist = sqrtf(d0 * d0 + d1 * d1 + d2 * d2);
+  hit = dist <= radius;
+  const float value = radius * radius - dist * dist;
+  const float chord = (value >= 0.f) ? 2.f * sqrtf(value) : 0.f;
+  const float cd = sqrtf((c[0] * c[0] + c[1] * c[1]) + c[2] * c[2]);
+  entry = (cd < radius) ? 0.f : sqrtf(cd * cd - dist * dist) - chord / 2.0f;
+  ex = entry + chord;
+}
+
+// sorted insertion into the per-ray top-B records (smallest |sdf| first); replaces topk over the step lists
+// (renderer.py:316-319)
+__device__ __forceinline__ void topk_insert(const dist_workspace_t& ws, int P, int B, int lp, float sdf, float px, float py,
+                                            float pz, float zafter, float zgen, int lvl) {
+  const float asdf = fabsf(sdf);
+  int pos = B;
+  for (int b = 0; b < B; ++b)
+    if (asdf < fabsf(ws.top_sdf[(size_t)b * P + lp])) { pos = b; break; }
+  if (pos >= B) return;
+  for (int b = B - 1; b > pos; --b) {
+    ws.top_sdf[(size_t)b * P + lp] = ws.top_sdf[(size_t)(b - 1) * P + lp];
+    ws.top_zafter[(size_t)b * P + lp] = ws.top_zafter[(size_t)(b - 1) * P + lp];
+    ws.top_zgen[(size_t)b * P + lp] = ws.top_zgen[(size_t)(b - 1) * P + lp];
+    ws.top_lvl[(size_t)b * P + lp] = ws.top_lvl[(size_t)(b - 1) * P + lp];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) ws.top_pt[((size_t)b * 3 + k) * P + lp] = ws.top_pt[((size_t)(b - 1) * 3 + k) * P + lp];
+  }
+  ws.top_sdf[(size_t)pos * P + lp] = sdf;
+  ws.top_zafter[(size_t)pos * P + lp] = zafter;
+  ws.top_zgen[(size_t)pos * P + lp] = zgen;
+  ws.top_lvl[(size_t)pos * P + lp] = (uint8_t)lvl;
+  ws.top_pt[((size_t)pos * 3 + 0) * P + lp] = px;
+  ws.top_pt[((size_t)pos * 3 + 1) * P + lp] = py;
+  ws.top_pt[((size_t)pos * 3 + 2) * P + lp] = pz;
+}
+
+// One coarse level of the pyramid (renderer.py:713-805): arrays carved from ws.pyr_{f,i,b}
+struct Level {
+  int w, h, P, scale;       // scale = 4 (1/4 resolution) or 2
+  float *ray, *start, *z, *s_sdf, *s_pt, *s_zabs, *s_zgen;   // [3][P], [P], [P], [3][P], [3][3][P], [3][P], [3][P]
+  uint8_t* hit;             // [P] max-pooled sphere-hit mask (renderer.py:668-680)
+  int32_t* list;            // [P]
+  int32_t* count;           // [1]
+};
 
 // p = M^T (c + ray * depth)   (renderer.py:202-223, :119)
 __device__ __forceinline__ void point_on_ray(const Cam& cam, const float (&c)[3], const float (&ray)[3], float depth,
@@ -61,52 +112,162 @@ __device__ __forceinline__ float clampf(float v, float c) { return fminf(fmaxf(v
 
 // ---------------------------------------------------------------------------------------------- set-up
 __global__ void k_setup(Cam cam, dist_march_t mp, dist_workspace_t ws, float* Zdepth, uint8_t* mask, float* min_sdf,
-                        int P) {
+                        int P, Level L1, Level L2) {
   const int lp = blockIdx.x * blockDim.x + threadIdx.x;
   const bool in = lp < P;
+  const bool pyr = mp.marching_type == DIST_MARCH_PYRAMID;
   float R[9], c[3];
 #pragma unroll
   for (int i = 0; i < 9; ++i) R[i] = cam.R[i];
 #pragma unroll
   for (int i = 0; i < 3; ++i) c[i] = cam.c[i];
   bool live = false;
-  float ray[3] = {0.f, 0.f, 1.f}, entry = 0.f;
+  float ray[3] = {0.f, 0.f, 1.f}, start = 0.f;
   if (in) {
     pixel_ray(cam, R, lp, ray);
-    // renderer.py:225-239
-    const float ptq = (c[0] * ray[0] + c[1] * ray[1]) + c[2] * ray[2];
-    const float d0 = c[0] - ptq * ray[0], d1 = c[1] - ptq * ray[1], d2 = c[2] - ptq * ray[2];
-    const float dist = sqrtf(d0 * d0 + d1 * d1 + d2 * d2);
-    const bool hit = dist <= cam.radius;
-    // renderer.py:241-273
-    const float value = cam.radius * cam.radius - dist * dist;
-    const float chord = (value >= 0.f) ? 2.f * sqrtf(value) : 0.f;
-    const float cd = sqrtf((c[0] * c[0] + c[1] * c[1]) + c[2] * c[2]);
-    entry = (cd < cam.radius) ? 0.f : sqrtf(cd * cd - dist * dist) - chord / 2.0f;
-    const float ex = entry + chord;
+    float dist, entry, ex;
+    bool hit;
+    sphere_geom(c, ray, cam.radius, dist, hit, entry, ex);
+    start = entry;
     ws.ray[lp] = ray[0]; ws.ray[P + lp] = ray[1]; ws.ray[2 * P + lp] = ray[2];
-    ws.entry[lp] = entry; ws.exit_[lp] = ex; ws.dist[lp] = dist; ws.z[lp] = 0.f;
+    ws.exit_[lp] = ex; ws.dist[lp] = dist; ws.z[lp] = 0.f;
     ws.flags[lp] = hit ? 1 : 0;
     ws.nreal[lp] = 0;
     for (int b = 0; b < mp.buffer_size; ++b) {
       ws.top_sdf[(size_t)b * P + lp] = 1.0f;  // filler entries: sdf 1, point 0 (renderer.py:539-540,555)
       ws.top_zafter[(size_t)b * P + lp] = 0.f;
       ws.top_zgen[(size_t)b * P + lp] = nanf("");
+      ws.top_lvl[(size_t)b * P + lp] = 0;
 #pragma unroll
       for (int k = 0; k < 3; ++k) ws.top_pt[((size_t)b * 3 + k) * P + lp] = 0.f;
     }
+    if (pyr) {
+      // the full-resolution march starts at the parent's last depth (renderer.py:769) and inherits the samples taken
+      // on the grandparent and parent rays (index up-sampling, renderer.py:787-801)
+      const int x = lp % cam.W, y = lp / cam.W;
+      const int p1 = (y >> 1) * L1.w + (x >> 1), p2 = (y >> 2) * L2.w + (x >> 2);
+      start = L1.start[p1] + (L1.hit[p1] ? L1.z[p1] : 0.f);
+      if (hit) {
+        for (int lv = 2; lv >= 1; --lv) {
+          const Level& L = (lv == 2) ? L2 : L1;
+          const int pp = (lv == 2) ? p2 : p1;
+          if (!L.hit[pp]) continue;
+          const int ns = mp.coarse_steps[2 - lv];
+          for (int st = 0; st < ns; ++st)
+            topk_insert(ws, P, mp.buffer_size, lp, L.s_sdf[(size_t)st * L.P + pp], L.s_pt[((size_t)st * 3 + 0) * L.P + pp],
+                        L.s_pt[((size_t)st * 3 + 1) * L.P + pp], L.s_pt[((size_t)st * 3 + 2) * L.P + pp],
+                        L.s_zabs[(size_t)st * L.P + pp] - entry, L.s_zgen[(size_t)st * L.P + pp], lv);
+        }
+      }
+    }
+    ws.entry[lp] = start; ws.entry0[lp] = entry;
     if (!hit) {
       Zdepth[lp] = 1e11f; mask[lp] = 0;
       min_sdf[lp] = dist + mp.threshold - cam.radius;  // renderer.py:863
     }
-    live = hit && (mp.marching_type == DIST_MARCH_TRIVIAL || (0.f + entry < ex));  // renderer.py:526
+    live = hit && (mp.marching_type == DIST_MARCH_TRIVIAL || (0.f + start < ex));  // renderer.py:526
   }
   const int idx = warp_append(ws.counts + 0, live);
   if (idx >= 0) {
     float p[3];
-    point_on_ray(cam, c, ray, entry + 0.f, p);
+    point_on_ray(cam, c, ray, start + 0.f, p);
     ws.list_a[idx] = lp;
     ws.pts[(size_t)idx * 3] = p[0]; ws.pts[(size_t)idx * 3 + 1] = p[1]; ws.pts[(size_t)idx * 3 + 2] = p[2];
+  }
+}
+
+// sphere-hit flags of the full image only (needed before the pyramid levels can be pooled)
+__global__ void k_hit_flags(Cam cam, dist_workspace_t ws, int P) {
+  const int lp = blockIdx.x * blockDim.x + threadIdx.x;
+  if (lp >= P) return;
+  float R[9], c[3], ray[3], dist, entry, ex;
+  bool hit;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) R[i] = cam.R[i];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) c[i] = cam.c[i];
+  pixel_ray(cam, R, lp, ray);
+  sphere_geom(c, ray, cam.radius, dist, hit, entry, ex);
+  ws.flags[lp] = hit ? 1 : 0;
+}
+
+// coarse level: rays through the pooled pixel centres, own sphere entry, max-pooled hit mask (renderer.py:604-680)
+__global__ void k_pyr_rays(Cam cam, Level L, const uint8_t* fine_hit, int fine_w, int fine_h, int fine_is_flags, float* maxentry) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= L.P) return;
+  const int ix = i % L.w, iy = i / L.w;
+  float R[9], c[3], ray[3], dist, entry, ex;
+  bool ownhit;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) R[k] = cam.R[k];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) c[k] = cam.c[k];
+  const float off = ((float)L.scale - 1.f) / 2.f;
+  coord_ray(cam, R, (float)L.scale * (float)ix + off, (float)L.scale * (float)iy + off, ray);
+  sphere_geom(c, ray, cam.radius, dist, ownhit, entry, ex);
+  L.ray[i] = ray[0]; L.ray[L.P + i] = ray[1]; L.ray[2 * L.P + i] = ray[2];
+  bool pooled = false;
+  for (int dy = 0; dy < 2; ++dy)
+    for (int dx = 0; dx < 2; ++dx) {
+      const int fx = 2 * ix + dx, fy = 2 * iy + dy;
+      if (fx < fine_w && fy < fine_h) pooled |= (fine_hit[fy * fine_w + fx] & 1) != 0;
+    }
+  (void)fine_is_flags;
+  L.hit[i] = pooled ? 1 : 0;
+  L.z[i] = 0.f;
+  // coarsest level: own entry where the coarse ray meets the sphere, else the largest entry of those that do
+  // (renderer.py:270-272); stash the own entry, resolve after the max is known
+  L.start[i] = ownhit ? entry : -1.f;
+  if (maxentry && ownhit) atomicMax(reinterpret_cast<int*>(maxentry), __float_as_int(fmaxf(entry, 0.f)));
+}
+
+// start depth of a coarse level + its (fixed) active list and first query points
+__global__ void k_pyr_start(Cam cam, Level L, Level parent, int has_parent, const float* maxentry, float* pts) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool on = false;
+  float start = 0.f;
+  if (i < L.P) {
+    if (has_parent) {
+      const int ix = i % L.w, iy = i / L.w, pp = (iy >> 1) * parent.w + (ix >> 1);
+      start = parent.start[pp] + (parent.hit[pp] ? parent.z[pp] : 0.f);   // renderer.py:769,779
+    } else {
+      start = (L.start[i] >= 0.f) ? L.start[i] : *maxentry;
+    }
+    L.start[i] = start;
+    on = L.hit[i] != 0;
+  }
+  const int idx = warp_append(L.count, on);
+  if (idx >= 0) {
+    float c[3], ray[3] = {L.ray[i], L.ray[L.P + i], L.ray[2 * L.P + i]}, p[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) c[k] = cam.c[k];
+    point_on_ray(cam, c, ray, start + 0.f, p);
+    L.list[idx] = i;
+    pts[(size_t)idx * 3] = p[0]; pts[(size_t)idx * 3 + 1] = p[1]; pts[(size_t)idx * 3 + 2] = p[2];
+  }
+}
+
+// one trivial march step of a coarse level (renderer.py:472-510 via :773): every listed ray advances, samples are
+// recorded per (step, ray); the query point of the next step overwrites this thread's own slot
+__global__ void k_pyr_step(Cam cam, dist_march_t mp, Level L, int step, float* pts, const float* sdfbuf) {
+  const int n = *L.count;
+  float c[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) c[k] = cam.c[k];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int id = L.list[i];
+    const float sdf = sdfbuf[i];
+    const float zc = L.z[id], start = L.start[id];
+    const float znew = zc + clampf(sdf, mp.clamp_dist) * mp.ratio;
+    L.z[id] = znew;
+    L.s_sdf[(size_t)step * L.P + id] = sdf;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) L.s_pt[((size_t)step * 3 + k) * L.P + id] = pts[(size_t)i * 3 + k];
+    L.s_zabs[(size_t)step * L.P + id] = znew + start;     // renderer.py:779
+    L.s_zgen[(size_t)step * L.P + id] = start + zc;
+    float ray[3] = {L.ray[id], L.ray[L.P + id], L.ray[2 * L.P + id]}, p[3];
+    point_on_ray(cam, c, ray, start + znew, p);
+    pts[(size_t)i * 3] = p[0]; pts[(size_t)i * 3 + 1] = p[1]; pts[(size_t)i * 3 + 2] = p[2];
   }
 }
 
@@ -144,27 +305,10 @@ __global__ void k_march_update(Cam cam, dist_march_t mp, dist_workspace_t ws, in
       ws.z[lp] = znew;
       ws.nreal[lp] = step + 1;
       if (step == 0 && sdf > mp.threshold) ws.flags[lp] |= 2;  // renderer.py:581
-      // insert into the sorted top-B (smallest |sdf| first); replaces topk over the step lists (renderer.py:316-319)
       const float asdf = fabsf(sdf);
-      int pos = B;
-      for (int b = 0; b < B; ++b)
-        if (asdf < fabsf(ws.top_sdf[(size_t)b * P + lp])) { pos = b; break; }
-      if (pos < B) {
-        for (int b = B - 1; b > pos; --b) {
-          ws.top_sdf[(size_t)b * P + lp] = ws.top_sdf[(size_t)(b - 1) * P + lp];
-          ws.top_zafter[(size_t)b * P + lp] = ws.top_zafter[(size_t)(b - 1) * P + lp];
-          ws.top_zgen[(size_t)b * P + lp] = ws.top_zgen[(size_t)(b - 1) * P + lp];
-#pragma unroll
-          for (int k = 0; k < 3; ++k)
-            ws.top_pt[((size_t)b * 3 + k) * P + lp] = ws.top_pt[((size_t)(b - 1) * 3 + k) * P + lp];
-        }
-        ws.top_sdf[(size_t)pos * P + lp] = sdf;
-        ws.top_zafter[(size_t)pos * P + lp] = znew;
-        ws.top_zgen[(size_t)pos * P + lp] = entry + zc;
-        ws.top_pt[((size_t)pos * 3 + 0) * P + lp] = px;
-        ws.top_pt[((size_t)pos * 3 + 1) * P + lp] = py;
-        ws.top_pt[((size_t)pos * 3 + 2) * P + lp] = pz;
-      }
+      // marching depth relative to the true sphere entry (renderer.py:800-804 for the pyramid variant)
+      const float zstore = (mp.marching_type == DIST_MARCH_PYRAMID) ? (znew + entry) - ws.entry0[lp] : znew;
+      topk_insert(ws, P, B, lp, sdf, px, py, pz, zstore, entry + zc, 0);
       if (step + 1 < mp.march_step) {
         if (mp.marching_type == DIST_MARCH_TRIVIAL) live = true;
         else live = (znew + entry < ws.exit_[lp]) && (asdf >= mp.threshold);  // renderer.py:559-561
@@ -197,7 +341,7 @@ __global__ void k_finalize(dist_march_t mp, dist_workspace_t ws, float* Zdepth, 
   const float so = ws.sdf_origin[0];
   const float zfin = ws.z[lp];
   // renderer.py:562-567: a global early break before buffer_size steps pads the lists with copies of the last step
-  if (S < B && nreal == S && nreal > 0) {
+  if (S < B && nreal == S && nreal > 0 && mp.marching_type != DIST_MARCH_PYRAMID) {
     int j = 0;
     for (int b = 0; b < nreal; ++b)
       if (ws.top_zafter[(size_t)b * P + lp] == zfin) j = b;
@@ -208,6 +352,7 @@ __global__ void k_finalize(dist_march_t mp, dist_workspace_t ws, float* Zdepth, 
       ws.top_zafter[(size_t)d * P + lp] = ws.top_zafter[(size_t)b * P + lp];
       ws.top_zgen[(size_t)d * P + lp] = ws.top_zgen[(size_t)b * P + lp];
       for (int k = 0; k < 3; ++k) ws.top_pt[((size_t)d * 3 + k) * P + lp] = ws.top_pt[((size_t)b * 3 + k) * P + lp];
+      ws.top_lvl[(size_t)d * P + lp] = 0;
     }
     for (int d = j + 1; d <= j + pad; ++d) {
       ws.top_sdf[(size_t)d * P + lp] = ws.top_sdf[(size_t)j * P + lp];
@@ -220,21 +365,23 @@ __global__ void k_finalize(dist_march_t mp, dist_workspace_t ws, float* Zdepth, 
   }
   const float s0 = ws.top_sdf[lp];
   const float entry = ws.entry[lp];
+  const bool real0 = (s0 != 1.0f);   // a filler record has sdf exactly 1 (tanh output is < 1)
   const bool first_ok = (nreal == 0) || (ws.flags[lp] & 2);
   const bool valid = (zfin + entry < ws.exit_[lp]) && (fabsf(s0) <= mp.threshold) &&
                      (!mp.first_query_check || first_ok);  // renderer.py:574-582
-  min_sdf[lp] = (nreal > 0) ? s0 : so;  // renderer.py:382-390 (value of the re-query at the min-|sdf| point)
+  min_sdf[lp] = real0 ? s0 : so;  // renderer.py:382-390 (value of the re-query at the min-|sdf| point)
   // renderer.py:407-408
   float zz = ws.top_zafter[lp] + (1.f - mp.ratio) * clampf(s0, mp.clamp_dist);
   if (mp.replay_grad_rounding) {  // renderer.py:414-417: z - s.detach()*ratio + s*ratio, value-neutral up to rounding
     for (int b = 0; b < B; ++b) {
-      const float s = clampf((b < nreal) ? ws.top_sdf[(size_t)b * P + lp] : so, mp.clamp_dist);
+      const float sb = ws.top_sdf[(size_t)b * P + lp];
+      const float s = clampf((sb != 1.0f) ? sb : so, mp.clamp_dist);
       const float a = s * mp.ratio;
       zz = zz - a;
       zz = zz + a;
     }
   }
-  Zdepth[lp] = entry + zz;  // renderer.py:868
+  Zdepth[lp] = ws.entry0[lp] + zz;  // renderer.py:868
   mask[lp] = valid ? 1 : 0;
 }
 
@@ -279,14 +426,14 @@ __global__ void k_bwd_gen(dist_march_t mp, dist_workspace_t ws, const float* gZ,
   const int lp = blockIdx.x * blockDim.x + threadIdx.x;
   const bool hit = lp < P && (ws.flags[lp] & 1);
   const int B = mp.buffer_size;
-  const int nreal = hit ? ws.nreal[lp] : 0;
   const float so = ws.sdf_origin[0];
   const float gz = (hit && gZ) ? gZ[lp] : 0.f;
   const float gm = (hit && gM) ? gM[lp] : 0.f;
   for (int b = 0; b < B; ++b) {
     float cf = 0.f;
     if (hit) {
-      const float s = (b < nreal) ? ws.top_sdf[(size_t)b * P + lp] : so;
+      const float sb = ws.top_sdf[(size_t)b * P + lp];
+      const float s = (sb != 1.0f) ? sb : so;
       const bool cm = (s >= -mp.clamp_dist) && (s <= mp.clamp_dist);
       cf = cm ? mp.ratio * gz : 0.f;  // renderer.py:414-417
       if (b == 0) cf += gm;           // renderer.py:386 (unclamped re-query at the min-|sdf| sample)
@@ -302,7 +449,8 @@ __global__ void k_bwd_gen(dist_march_t mp, dist_workspace_t ws, const float* gZ,
 }
 
 __global__ void k_bwd_scatter(Cam cam, dist_workspace_t ws, const int32_t* row_pix, const float* dpts,
-                              const int32_t* count, float* d_cam, float* d_ray, int P) {
+                              const int32_t* count, float* d_cam, float* d_ray, float* d_ray_coarse, int w1, int P1, int w2,
+                              int P2, int P) {
   const int n = *count;
   float acc[3] = {0.f, 0.f, 0.f};
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -314,7 +462,13 @@ __global__ void k_bwd_scatter(Cam cam, dist_workspace_t ws, const int32_t* row_p
     for (int k = 0; k < 3; ++k) {  // p = M^T q  ->  dL/dq = M dL/dp
       const float v = fmaf(cam.M[k * 3 + 2], d[2], fmaf(cam.M[k * 3 + 1], d[1], cam.M[k * 3] * d[0]));
       acc[k] += v;
-      atomicAdd(d_ray + (size_t)k * P + lp, v * zg);
+      const int lvl = ws.top_lvl[(size_t)b * P + lp];
+      if (lvl == 0) atomicAdd(d_ray + (size_t)k * P + lp, v * zg);
+      else if (d_ray_coarse) {   // sample taken on the parent (1/2) or grandparent (1/4 resolution) ray
+        const int x = lp % cam.W, y = lp / cam.W;
+        if (lvl == 1) atomicAdd(d_ray_coarse + (size_t)k * P1 + (y >> 1) * w1 + (x >> 1), v * zg);
+        else atomicAdd(d_ray_coarse + (size_t)3 * P1 + (size_t)k * P2 + (y >> 2) * w2 + (x >> 2), v * zg);
+      }
     }
   }
 #pragma unroll
@@ -339,7 +493,32 @@ int make_cam(const dist_camera_t* cam, Cam* out) {
 }  // namespace
 
 // =============================================================================================== host entry points
-int render_depth_fwd(const dist_net_t* net, int engine, const dist_camera_t* camh, const dist_march_t* mp,
+static void carve_levels(const Cam& cam, const dist_workspace_t* ws, Level* L1, Level* L2) {
+  Level* Ls[2] = {L1, L2};
+  int w = cam.W, h = cam.n_rows;
+  float* f = ws->pyr_f;
+  int32_t* li = ws->pyr_i;
+  uint8_t* bb = ws->pyr_b;
+  const int w1 = (w + 1) / 2, h1 = (h + 1) / 2, w2 = (w1 + 1) / 2, h2 = (h1 + 1) / 2;
+  const int dims[2][2] = {{w1, h1}, {w2, h2}};
+  int32_t* counts = li + (size_t)w1 * h1 + (size_t)w2 * h2;
+  for (int i = 0; i < 2; ++i) {
+    Level& L = *Ls[i];
+    L.w = dims[i][0]; L.h = dims[i][1]; L.P = L.w * L.h; L.scale = (i == 0) ? 2 : 4;
+    L.ray = f; f += 3 * (size_t)L.P;
+    L.start = f; f += L.P;
+    L.z = f; f += L.P;
+    L.s_sdf = f; f += 3 * (size_t)L.P;
+    L.s_pt = f; f += 9 * (size_t)L.P;
+    L.s_zabs = f; f += 3 * (size_t)L.P;
+    L.s_zgen = f; f += 3 * (size_t)L.P;
+    L.hit = bb; bb += L.P;
+    L.list = li; li += L.P;
+    L.count = counts + i;
+  }
+}
+
+int render_depth_fwd(const dist_net_t* net, int engine, const dist_camera_t* camh, const dist_march_t* mp_in,
                      const dist_workspace_t* ws, float* Zdepth, uint8_t* mask, float* min_sdf, int64_t* rows_eval,
                      cudaStream_t st) {
   Cam cam;
@@ -348,14 +527,47 @@ int render_depth_fwd(const dist_net_t* net, int engine, const dist_camera_t* cam
   NetDev nd;
   rc = make_netdev(net, &nd);
   if (rc) return rc;
+  dist_march_t mpv = *mp_in;
+  dist_march_t* mp = &mpv;
   DIST_REQUIRE(mp->buffer_size >= 1 && mp->buffer_size <= DIST_MAX_BUFFER, "buffer_size must be in [1,%d]", DIST_MAX_BUFFER);
   DIST_REQUIRE(mp->march_step >= 1, "march_step must be >= 1");
-  DIST_REQUIRE(mp->marching_type == DIST_MARCH_TRIVIAL || mp->marching_type == DIST_MARCH_RECURSIVE, "bad marching_type");
+  DIST_REQUIRE(mp->marching_type >= DIST_MARCH_TRIVIAL && mp->marching_type <= DIST_MARCH_PYRAMID, "bad marching_type");
+  DIST_REQUIRE(ws->entry0 && ws->top_lvl, "workspace: entry0 / top_lvl missing");
+  const bool pyr = mp->marching_type == DIST_MARCH_PYRAMID;
   const int P = cam.W * cam.n_rows;
-  const int S = mp->march_step;
-  DIST_CHECK_CUDA(cudaMemsetAsync(ws->counts, 0, sizeof(int32_t) * (S + 2), st));
+  const int S_total = mp->march_step;
   const int tb = 256, gb = (P + tb - 1) / tb;
-  k_setup<<<gb, tb, 0, st>>>(cam, *mp, *ws, Zdepth, mask, min_sdf, P); count_launch();
+  Level L1, L2;
+  memset(&L1, 0, sizeof(L1)); memset(&L2, 0, sizeof(L2));
+  if (pyr) {
+    DIST_REQUIRE(ws->pyr_f && ws->pyr_i && ws->pyr_b, "workspace: pyramid buffers missing");
+    DIST_REQUIRE(cam.row0 == 0 && cam.row_step == 1 && cam.n_rows == cam.H, "pyramid marching needs the full image (no row bands)");
+    DIST_REQUIRE(mp->coarse_steps[0] >= 1 && mp->coarse_steps[0] <= 3 && mp->coarse_steps[1] >= 1 && mp->coarse_steps[1] <= 3 &&
+                     mp->coarse_steps[0] + mp->coarse_steps[1] < S_total, "pyramid marching: coarse step counts must be in [1,3]");
+    carve_levels(cam, ws, &L1, &L2);
+    mp->march_step = S_total - mp->coarse_steps[0] - mp->coarse_steps[1];   // renderer.py:724-725
+    mp->first_query_check = 0;                                               // renderer.py:795
+    float* maxentry = reinterpret_cast<float*>(L1.count + 2);
+    DIST_CHECK_CUDA(cudaMemsetAsync(L1.count, 0, sizeof(int32_t) * 8, st));
+    k_hit_flags<<<gb, tb, 0, st>>>(cam, *ws, P); count_launch();
+    k_pyr_rays<<<(L1.P + tb - 1) / tb, tb, 0, st>>>(cam, L1, ws->flags, cam.W, cam.n_rows, 1, nullptr); count_launch();
+    k_pyr_rays<<<(L2.P + tb - 1) / tb, tb, 0, st>>>(cam, L2, L1.hit, L1.w, L1.h, 0, maxentry); count_launch();
+    for (int lv = 2; lv >= 1; --lv) {
+      Level& L = (lv == 2) ? L2 : L1;
+      k_pyr_start<<<(L.P + tb - 1) / tb, tb, 0, st>>>(cam, L, L2, lv == 1 ? 1 : 0, maxentry, ws->pts); count_launch();
+      const int ns = mp->coarse_steps[2 - lv];
+      for (int s = 0; s < ns; ++s) {
+        MlpArgs a{};
+        a.points = ws->pts; a.n_host = L.P; a.n_dev = L.count; a.clamp_dist = 0.f; a.sdf = ws->sdf; a.rows_evaluated = rows_eval;
+        rc = mlp_launch(net, nd, engine, 0, a, st);
+        if (rc) return rc;
+        k_pyr_step<<<min((L.P + tb - 1) / tb, 4 * num_sms()), tb, 0, st>>>(cam, *mp, L, s, ws->pts, ws->sdf); count_launch();
+      }
+    }
+  }
+  const int S = mp->march_step;
+  DIST_CHECK_CUDA(cudaMemsetAsync(ws->counts, 0, sizeof(int32_t) * (S_total + 2), st));
+  k_setup<<<gb, tb, 0, st>>>(cam, *mp, *ws, Zdepth, mask, min_sdf, P, L1, L2); count_launch();
   k_append_origin<<<1, 1, 0, st>>>(*ws, S + 1); count_launch();
   DIST_CHECK_CUDA(cudaGetLastError());
   const int gu = min(gb, 4 * num_sms());
@@ -399,7 +611,7 @@ int render_normal_fwd(const dist_net_t* net, int engine, const dist_camera_t* ca
 
 int render_depth_bwd(const dist_net_t* net, int engine, const dist_camera_t* camh, const dist_march_t* mp,
                      const dist_workspace_t* ws, const float* gZ, const float* gM, float* acc0, float* accl,
-                     float* d_cam, float* d_ray, int32_t* s_row_pix, float* s_pts, float* s_coef, uint8_t* s_clamp,
+                     float* d_cam, float* d_ray, float* d_ray_coarse, int32_t* s_row_pix, float* s_pts, float* s_coef, uint8_t* s_clamp,
                      float* s_dpts, int32_t* s_count, int64_t* rows_eval, cudaStream_t st) {
   (void)s_clamp;
   Cam cam;
@@ -418,8 +630,9 @@ int render_depth_bwd(const dist_net_t* net, int engine, const dist_camera_t* cam
   rc = mlp_launch(net, nd, engine, 2, a, st);
   if (rc) return rc;
   if (d_cam && d_ray) {
+    const int w1 = (cam.W + 1) / 2, h1 = (cam.n_rows + 1) / 2, w2 = (w1 + 1) / 2, h2 = (h1 + 1) / 2;
     k_bwd_scatter<<<min((int)(((int64_t)P * mp->buffer_size + tb - 1) / tb), 4 * num_sms()), tb, 0, st>>>(
-        cam, *ws, s_row_pix, s_dpts, s_count, d_cam, d_ray, P); count_launch();
+        cam, *ws, s_row_pix, s_dpts, s_count, d_cam, d_ray, d_ray_coarse, w1, w1 * h1, w2, w2 * h2, P); count_launch();
   }
   DIST_CHECK_CUDA(cudaGetLastError());
   return DIST_OK;

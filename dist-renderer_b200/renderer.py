@@ -7,8 +7,8 @@ launches on the current stream and chains the tiny camera Jacobian (c = -R^T T, 
 
 Differences from the reference, all loud:
   * no CPU path: ``use_gpu=False`` or a CPU decoder raises;
-  * ``ray_marching_type='pyramid_recursive'``, ``use_depth2normal``, ``num_forward_sampling``
-    and ``sample_index_type != 'min_abs'`` raise NotImplementedError;
+  * ``use_depth2normal``, ``num_forward_sampling`` and ``sample_index_type != 'min_abs'`` raise NotImplementedError;
+    ``pyramid_recursive`` is implemented for the default ``scale_list=[4,2,1]`` on full images;
   * 3x4 ``transform_matrix`` raises (the reference's own 3x4 inverse path calls an un-imported ``pdb``);
   * when no ray meets the unit sphere the reference dies inside ``.max()`` of an empty tensor; here
     ``ValueError('No valid depth.')`` (renderer.py:215) is raised;
@@ -23,7 +23,7 @@ from .functional import resolve_engine, DEFAULT_ENGINE
 from .plan import plan_for
 
 _MARCH = {"trivial": _abi.MARCH_TRIVIAL, "trivial_non_parallel": _abi.MARCH_TRIVIAL,
-          "recursive": _abi.MARCH_RECURSIVE}
+          "recursive": _abi.MARCH_RECURSIVE, "pyramid_recursive": _abi.MARCH_PYRAMID}
 
 
 def _stream():
@@ -47,18 +47,22 @@ class _RenderDepthFn(torch.autograd.Function):
         cam = ren._c_camera(Rd, cam_pos, opts["use_transform"])
         mp = _abi.March(ren.march_step, B, _MARCH[opts["kind"]], 1 if opts["kind"] != "pyramid_recursive" else 0,
                         ren.ray_marching_ratio, ren.threshold, float(opts["clamp_dist"]), 1 if opts["replay"] else 0)
+        pyr = opts["kind"] == "pyramid_recursive"
+        if pyr:
+            mp.coarse_steps[0], mp.coarse_steps[1] = ren._coarse_steps()
         f32 = dict(device=dev, dtype=torch.float32)
         saved = {
             "flags": torch.empty(P, device=dev, dtype=torch.uint8), "nreal": torch.empty(P, device=dev, dtype=torch.int32),
             "top_sdf": torch.empty(B, P, **f32), "top_pt": torch.empty(B, 3, P, **f32),
             "top_zafter": torch.empty(B, P, **f32), "top_zgen": torch.empty(B, P, **f32),
             "sdf_origin": torch.empty(1, **f32), "dist": torch.empty(P, **f32),
+            "top_lvl": torch.empty(B, P, device=dev, dtype=torch.uint8),
         }
-        scr = ren._scratch()
+        scr = ren._scratch(pyramid=pyr)
         ws = _abi.Workspace()
         for name in _abi.WS_FIELDS:
             t = saved.get(name, scr.get(name))
-            setattr(ws, name, t.data_ptr())
+            setattr(ws, name, t.data_ptr() if t is not None else None)
         Zdepth = torch.empty(P, **f32)
         mask = torch.empty(P, device=dev, dtype=torch.uint8)
         min_sdf = torch.empty(P, **f32)
@@ -86,7 +90,8 @@ class _RenderDepthFn(torch.autograd.Function):
         ws = _abi.Workspace()
         for name in _abi.WS_FIELDS:
             t = ctx.saved.get(name, scr.get(name))
-            setattr(ws, name, t.data_ptr())
+            setattr(ws, name, t.data_ptr() if t is not None else None)
+        pyr = opts["kind"] == "pyramid_recursive"
         gZ = gZ.contiguous().float() if (gZ is not None and opts["want_depth_grad"]) else None
         gM = gM.contiguous().float() if (gM is not None and opts["want_mask_grad"]) else None
         want_cam = opts["want_camera_grad"] and (ctx.needs_input_grad[1] or ctx.needs_input_grad[2])
@@ -95,12 +100,14 @@ class _RenderDepthFn(torch.autograd.Function):
         accl = torch.zeros(plan.bias[plan.latent_in].numel(), **f32) if plan.latent_in >= 0 else None
         d_cam = torch.zeros(3, **f32) if want_cam else None
         d_ray = torch.zeros(3, P, **f32) if want_cam else None
+        n_coarse = sum(g[0].shape[1] for g in ren._coarse_homo()) if (want_cam and pyr) else 0
+        d_ray_c = torch.zeros(3 * n_coarse, **f32) if n_coarse else None
         g_lat = g_R = g_T = None
         if gZ is not None or gM is not None:
             s_row, s_pts, s_coef, s_dpts, s_cnt = scr["b_row"], scr["b_pts"], scr["b_coef"], scr["b_dpts"], scr["b_cnt"]
             _abi.check(lib.dist_render_depth_bwd(net, ctx.engine, cam, ctx.mp, ws, _abi.ptr(gZ), _abi.ptr(gM),
                                                  _abi.ptr(acc0), _abi.ptr(accl), _abi.ptr(d_cam), _abi.ptr(d_ray),
-                                                 _abi.ptr(s_row), _abi.ptr(s_pts), _abi.ptr(s_coef), None,
+                                                 _abi.ptr(d_ray_c), _abi.ptr(s_row), _abi.ptr(s_pts), _abi.ptr(s_coef), None,
                                                  _abi.ptr(s_dpts), _abi.ptr(s_cnt), _abi.ptr(ren.rows_grad), st))
             if ctx.needs_input_grad[0] and latent is not None:
                 g_lat = plan.latent_grad(acc0, accl).reshape(latent.shape).to(latent.dtype)
@@ -108,8 +115,15 @@ class _RenderDepthFn(torch.autograd.Function):
                 with torch.enable_grad():
                     Rg, Tg = Rd.clone().requires_grad_(True), Td.clone().requires_grad_(True)
                     c = torch.matmul(-Rg.t(), Tg[:, None]).squeeze(1)
-                    rays = ren.get_camera_rays(Rg)
-                    g_R, g_T = torch.autograd.grad([c, rays], [Rg, Tg], [d_cam, d_ray], allow_unused=True)
+                    outs, gouts = [c, ren.get_camera_rays(Rg)], [d_cam, d_ray]
+                    if d_ray_c is not None:   # samples taken on the 1/2- and 1/4-resolution parent rays
+                        off = 0
+                        for (homo,) in ren._coarse_homo():
+                            n_l = homo.shape[1]
+                            outs.append(ren.get_camera_rays(Rg, homo=homo))
+                            gouts.append(d_ray_c[off:off + 3 * n_l].reshape(3, n_l))
+                            off += 3 * n_l
+                    g_R, g_T = torch.autograd.grad(outs, [Rg, Tg], gouts, allow_unused=True)
         return g_lat, g_R, g_T, None, None
 
 
@@ -245,14 +259,49 @@ class SDFRenderer(object):
         cam.radius = self.radius
         return cam
 
-    def _scratch(self):
+    def _coarse_steps(self):
+        """(steps at 1/4 resolution, steps at 1/2 resolution) of the pyramid march (renderer.py:13,724-726)."""
+        if list(self.scale_list) != [4, 2, 1] or len(self.march_step_list) != 3 or self.march_step_list[2] != -1:
+            raise NotImplementedError("pyramid_recursive is implemented for scale_list=[4,2,1], march_step_list=[a,b,-1]")
+        a, b = int(self.march_step_list[0]), int(self.march_step_list[1])
+        if not (1 <= a <= 3 and 1 <= b <= 3 and a + b < self.march_step):
+            raise NotImplementedError("pyramid_recursive: coarse step counts must be in [1,3]")
+        return a, b
+
+    def _coarse_dims(self):
+        h, w = self.local_hw
+        h1, w1 = (h + 1) // 2, (w + 1) // 2
+        h2, w2 = (h1 + 1) // 2, (w1 + 1) // 2
+        return (h1, w1), (h2, w2)
+
+    def _coarse_homo(self):
+        """K^-1 [xc, yc, 1] of the pooled pixel centres of the 1/2 and 1/4 resolution levels (renderer.py:604-636)."""
+        if getattr(self, "_chomo", None) is None:
+            res = []
+            for (hh, ww), scale in zip(self._coarse_dims(), (2.0, 4.0)):
+                ys = scale * torch.arange(hh, device=self.device).float() + (scale - 1) / 2
+                xs = scale * torch.arange(ww, device=self.device).float() + (scale - 1) / 2
+                Y, X = torch.meshgrid(ys, xs, indexing="ij")
+                homo = torch.stack([X.reshape(-1), Y.reshape(-1), torch.ones(hh * ww, device=self.device)], 0)
+                res.append((torch.matmul(self.K_inv, homo),))
+            self._chomo = res
+        return self._chomo
+
+    def _scratch(self, pyramid=False):
         """Reusable (not saved-for-backward) per-renderer device scratch, stream-ordered."""
+        if pyramid and self._scr is not None and self._scr.get("pyr_f") is None:
+            (h1, w1), (h2, w2) = self._coarse_dims()
+            npc = h1 * w1 + h2 * w2
+            self._scr["pyr_f"] = torch.empty(23 * npc, device=self.device, dtype=torch.float32)
+            self._scr["pyr_i"] = torch.empty(npc + 8, device=self.device, dtype=torch.int32)
+            self._scr["pyr_b"] = torch.empty(npc, device=self.device, dtype=torch.uint8)
         if self._scr is None:
             P, dev = self.P, self.device
             f32 = dict(device=dev, dtype=torch.float32)
             i32 = dict(device=dev, dtype=torch.int32)
             self._scr = {
                 "ray": torch.empty(3, P, **f32), "entry": torch.empty(P, **f32), "exit_": torch.empty(P, **f32),
+                "entry0": torch.empty(P, **f32), "pyr_f": None, "pyr_i": None, "pyr_b": None,
                 "z": torch.empty(P, **f32), "list_a": torch.empty(P, **i32), "list_b": torch.empty(P, **i32),
                 "pts": torch.empty(2, P + 1, 3, **f32), "sdf": torch.empty(P + 1, **f32),
                 "counts": torch.empty(self.march_step + 2, **i32),
@@ -263,6 +312,8 @@ class SDFRenderer(object):
                 "b_coef": torch.empty(P * self.buffer_size, **f32), "b_dpts": torch.empty(P * self.buffer_size, 3, **f32),
                 "b_cnt": torch.empty(1, **i32),
             }
+            if pyramid:
+                return self._scratch(pyramid=True)
         return self._scr
 
     def _raise_if_empty(self):
@@ -288,8 +339,9 @@ class SDFRenderer(object):
         if sample_index_type != 'min_abs':
             raise NotImplementedError("sample_index_type='%s' is not implemented (only 'min_abs')" % sample_index_type)
         if ray_marching_type == 'pyramid_recursive':
-            raise NotImplementedError("ray_marching_type='pyramid_recursive' is not implemented yet "
-                                      "(use 'recursive' or 'trivial')")
+            self._coarse_steps()
+            if self.rows != (0, 1, self.img_hw[0]):
+                raise NotImplementedError("pyramid_recursive needs the full image (row bands use 'recursive')")
         if ray_marching_type not in _MARCH:
             raise ValueError('Error! Invalid type of ray marching: {}.'.format(ray_marching_type))  # renderer.py:834
         any_grad = torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (latent, R, T))

@@ -33,7 +33,7 @@ enum {
   DIST_E_UNSUPPORTED = 3 /* feature not available in this build (e.g. tensor path on a non-sm_100 device) */
 };
 
-enum { DIST_MARCH_TRIVIAL = 0, DIST_MARCH_RECURSIVE = 1 };
+enum { DIST_MARCH_TRIVIAL = 0, DIST_MARCH_RECURSIVE = 1, DIST_MARCH_PYRAMID = 2 };
 
 /* Evaluation engines for the decoder rows. */
 enum {
@@ -98,6 +98,7 @@ typedef struct dist_march {
   float threshold;
   float clamp_dist;
   int32_t replay_grad_rounding; /* 1: reproduce the value-neutral (z - a) + a roundings of renderer.py:414-417 */
+  int32_t coarse_steps[2];    /* DIST_MARCH_PYRAMID: trivial steps at 1/4 and 1/2 resolution (renderer.py:13 march_step_list) */
 } dist_march_t;
 
 /*
@@ -122,6 +123,14 @@ typedef struct dist_workspace {
   float* sdf;        /* [P+1] decoder outputs of the current step */
   int32_t* counts;   /* [march_step + 2] active rays per step; zeroed by dist_render_depth_fwd */
   float* sdf_origin; /* [1] sdf at the origin (filler samples, renderer.py:539-540) */
+  float* entry0;     /* [P] true unit-sphere entry depth; == entry except in DIST_MARCH_PYRAMID, where `entry` holds the
+                        depth the full-resolution march starts from (inherited from the 1/2-resolution parent ray) */
+  uint8_t* top_lvl;  /* [B][P] pyramid level the sample was taken at (0 = this ray; 1, 2 = parent / grandparent ray) */
+  /* DIST_MARCH_PYRAMID only (renderer.py:713-805).  With (w1,h1) = ceil((w,h)/2), (w2,h2) = ceil((w1,h1)/2),
+   * P1 = w1*h1, P2 = w2*h2:  pyr_f: 23*(P1+P2) floats, pyr_i: (P1+P2)+8 int32, pyr_b: (P1+P2) bytes. */
+  float* pyr_f;
+  int32_t* pyr_i;
+  uint8_t* pyr_b;
 } dist_workspace_t;
 
 /* ---- library ---- */
@@ -178,10 +187,12 @@ int dist_render_normal_fwd(const dist_net_t* net, int engine, const dist_camera_
 /* Backward of dist_render_depth_fwd for upstream gZ[P] (on Zdepth) and gM[P] (on min_sdf; only sphere-hit pixels are
  * used): replays the saved top-B sample points.  Outputs acc0/accl as in dist_decoder_backward, d_cam_pos[3] and
  * d_ray[3][P] (gradient w.r.t. camera centre and per-pixel unit ray, for the host-side camera chain).
- * Either gZ or gM may be NULL.  scratch_* hold the compacted replay rows: rows up to P*buffer_size. */
+ * Either gZ or gM may be NULL.  scratch_* hold the compacted replay rows: rows up to P*buffer_size.
+ * d_ray_coarse ([3][P1] then [3][P2], DIST_MARCH_PYRAMID with camera gradients only, else NULL): gradient w.r.t. the
+ * unit rays of the 1/2- and 1/4-resolution pixel centres for samples taken on parent rays. */
 int dist_render_depth_bwd(const dist_net_t* net, int engine, const dist_camera_t* cam, const dist_march_t* mp,
                           const dist_workspace_t* ws, const float* gZ, const float* gM, float* acc0, float* accl,
-                          float* d_cam_pos, float* d_ray, int32_t* scratch_row_pix, float* scratch_pts,
+                          float* d_cam_pos, float* d_ray, float* d_ray_coarse, int32_t* scratch_row_pix, float* scratch_pts,
                           float* scratch_coef, uint8_t* scratch_clamp, float* scratch_dpts, int32_t* scratch_count,
                           int64_t* rows_evaluated, void* stream);
 

@@ -28,6 +28,10 @@ CASES = {
     "ragged_37x53": dict(decoder="B", hw=(37, 53), cam=("lookat", 200.0, -30.0, 1.9, 1.0), march_step=30,
                          buffer_size=5, kind="recursive"),
     "inside_32": dict(decoder="B", hw=(32, 32), cam=("front", 0.8), march_step=40, buffer_size=5, kind="recursive"),
+    "pyramid_ragged_37x53": dict(decoder="B", hw=(37, 53), cam=("lookat", 120.0, 20.0, 2.2, 1.3), march_step=50,
+                                 buffer_size=3, kind="pyramid_recursive"),
+    "pyramid_inside_30": dict(decoder="B", hw=(30, 30), cam=("front", 0.85), march_step=40, buffer_size=5,
+                              kind="pyramid_recursive"),
 }
 
 _DEC = {}

@@ -14,7 +14,7 @@ import gpu_util as gu
 
 pytestmark = pytest.mark.gpu
 pkg = cases.pkg
-RENDER_CASES = [n for n in sorted(cases.CASES) if cases.CASES[n]["kind"] != "pyramid_recursive"]
+RENDER_CASES = sorted(cases.CASES)
 
 
 @pytest.fixture(scope="session", autouse=True)
@@ -207,7 +207,9 @@ def test_api_errors():
     ren = pkg.SDFRenderer(dec, K, img_hw=(16, 16))
     lat = cases.synth.make_latent().cuda()
     with pytest.raises(NotImplementedError):
-        ren.render(lat, R.cuda(), T.cuda())            # default pyramid_recursive: not implemented yet, loudly
+        pkg.SDFRenderer(dec, K, img_hw=(16, 16), scale_list=[2, 1], march_step_list=[3, -1]).render(lat, R.cuda(), T.cuda())
+    with pytest.raises(NotImplementedError):
+        ren.render(lat, R.cuda(), T.cuda(), num_forward_sampling=2)
     with pytest.raises(ValueError):
         ren.render_depth(lat, R.cuda(), T.cuda(), ray_marching_type="bogus")
     with pytest.raises(RuntimeError):
