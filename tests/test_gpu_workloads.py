@@ -1,0 +1,116 @@
+"""GPU: the BASELINE.json configurations as workloads -- full-size properties (512x512), the single-view inverse
+optimisation loop (config 3) against the oracle's own trajectory, and the 24-view ring (config 4)."""
+import copy
+
+import pytest
+import torch
+
+import cases
+import gpu_util as gu
+from oracle.sdf_oracle import OracleSDFRenderer
+
+pytestmark = pytest.mark.gpu
+pkg = cases.pkg
+synth = cases.synth
+
+
+def _loss_mix(out, gt):
+    """Depth / normal / silhouette mix in the spirit of loss_single.compute_all_loss (weights 10/5/1)."""
+    depth, normal, mask, min_sdf = out
+    gdepth, gnormal, gmask = gt
+    both = mask.bool() & gmask.bool()
+    l_depth = (depth[both] - gdepth[both]).abs().mean() if bool(both.any()) else depth.sum() * 0
+    l_normal = (1 - (normal[both] * gnormal[both]).sum(-1)).mean() if bool(both.any()) else normal.sum() * 0
+    inside = gmask.bool()
+    l_mask = torch.relu(min_sdf[inside]).mean() + torch.relu(-min_sdf[~inside] + 1e-3).mean()
+    return 10.0 * l_depth + 5.0 * l_normal + 1.0 * l_mask
+
+
+def test_full_size_512_properties():
+    """512x512 (BASELINE config 2): size-independent properties instead of the (minutes-long) CPU oracle:
+    determinism, tensor-core vs exact-fp32 engine, row-band sharding == full image, output contracts."""
+    dec = gu.gpu_decoder("B")
+    H = W = 512
+    K, (R, T) = synth.intrinsic(H, W), synth.front_camera()
+    lat = synth.make_latent().cuda()
+    R, T = R.cuda(), T.cuda()
+    ren = pkg.SDFRenderer(dec, K, img_hw=(H, W), engine="tc")
+    a = ren.render(lat, R, T, ray_marching_type="recursive", no_grad=True)
+    b = ren.render(lat, R, T, ray_marching_type="recursive", no_grad=True)
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)                                   # deterministic
+    depth, normal, mask, min_sdf = a
+    assert depth.shape == (H, W) and normal.shape == (H, W, 3) and mask.dtype == torch.uint8
+    m = mask.bool()
+    assert 0.15 < float(m.float().mean()) < 0.35                   # the synthetic shape covers ~24 % of the image
+    assert bool((depth[~m] == 1e11).all()) and bool((normal[~m] == 0).all())
+    assert float((normal[m].norm(dim=-1) - 1).abs().max()) < 1e-5   # unit normals on the surface
+    assert float(min_sdf[m].abs().max()) <= ren.threshold + 1e-9    # converged rays sit below the threshold
+    assert float(depth[m].min()) > 0.9 and float(depth[m].max()) < 2.0
+    s = pkg.SDFRenderer(dec, K, img_hw=(H, W), engine="simt").render(lat, R, T, ray_marching_type="recursive", no_grad=True)
+    res = gu.compare([t.cpu() for t in a], [t.cpu() for t in s], max_xor=12)   # 262 K rays: a few threshold flips
+    print("512x512 tc vs simt:", res)
+    part = pkg.SDFRenderer(dec, K, img_hw=(H, W), engine="tc", rows=(3, 8, 64)).render(lat, R, T, ray_marching_type="recursive",
+                                                                                        no_grad=True)
+    for x, y in zip(part, a):
+        assert torch.equal(x, y[3::8])
+    p = ren.render(lat, R, T, no_grad=True)                        # default marching = pyramid_recursive
+    assert int((p[2] != a[2]).sum()) <= 0.002 * H * W              # pyramid vs recursive: +-1 pixel at silhouettes
+    mm = p[2].bool() & m
+    assert gu.rel(p[0][mm], a[0][mm]) < 1e-3
+
+
+def test_inverse_optimisation_tracks_oracle():
+    """Config 3 (run_single_shape path): Adam on the 256-d shape code through render() + loss + backward.
+    The CUDA path and the CPU oracle start from the same code and must follow the same loss trajectory."""
+    hw = (32, 32)
+    K, (R, T) = synth.intrinsic(*hw), synth.lookat_camera(30.0, 20.0, 1.6)
+    dec_c, dec_g = cases.decoder("B"), gu.gpu_decoder("B")
+    gt_lat = synth.make_latent(seed=2)
+    ora = OracleSDFRenderer(dec_c, K, img_hw=hw, march_step=60, buffer_size=3)
+    gt = [t.detach() for t in ora.render(gt_lat, R, T, no_grad=True)[:3]]
+    ren = pkg.SDFRenderer(dec_g, K, img_hw=hw, march_step=60, buffer_size=3)
+    gt_g = [t.cuda() for t in gt]
+
+    def run(render, lat0, R_, T_, gt_, n):
+        lat = lat0.clone().requires_grad_(True)
+        opt = torch.optim.Adam([lat], lr=1e-3)
+        losses = []
+        for _ in range(n):
+            opt.zero_grad()
+            loss = _loss_mix(render(lat, R_, T_), gt_)
+            loss.backward()
+            opt.step()
+            losses.append(float(loss))
+        return losses, lat.detach()
+    lat0 = synth.make_latent(seed=1)
+    l_cpu, z_cpu = run(lambda l, r, t: ora.render(l, r, t), lat0, R, T, gt, 6)
+    l_gpu, z_gpu = run(lambda l, r, t: ren.render(l, r, t), lat0.cuda(), R.cuda(), T.cuda(), gt_g, 6)
+    print("loss cpu", l_cpu, "gpu", l_gpu)
+    for a, b in zip(l_gpu, l_cpu):
+        assert abs(a - b) <= 2e-3 * abs(b) + 1e-6
+    assert gu.rel(z_gpu.cpu(), z_cpu) < 1e-3
+    l_long, _ = run(lambda l, r, t: ren.render(l, r, t), lat0.cuda(), R.cuda(), T.cuda(), gt_g, 40)
+    assert l_long[-1] < 0.9 * l_long[0]                            # the optimisation makes progress
+
+
+def test_multi_view_ring_gradients():
+    """Config 4 layout: views on a ring, summed loss, ONE backward over the shared code; vs the oracle on 3 views."""
+    hw = (24, 24)
+    views = synth.ring_cameras(24, 25.0, 2.5)[::8]
+    K = synth.intrinsic(*hw, focal_scale=1.2 * 2.5 / 1.6)
+    dec_c, dec_g = cases.decoder("B"), gu.gpu_decoder("B")
+    ora = OracleSDFRenderer(dec_c, K, img_hw=hw, march_step=50, buffer_size=5)
+    ren = pkg.SDFRenderer(dec_g, K, img_hw=hw, march_step=50, buffer_size=5)
+    l_c = synth.make_latent().requires_grad_(True)
+    l_g = synth.make_latent().cuda().requires_grad_(True)
+    outs_c = [ora.render(l_c, R, T) for R, T in views]
+    outs_g = [ren.render(l_g, R.cuda(), T.cuda()) for R, T in views]
+    flips = 0
+    for oc, og in zip(outs_c, outs_g):
+        res = gu.compare([t.detach().cpu() for t in og], [t.detach() for t in oc])
+        flips += res["xor"]
+    sum(cases.scalar_loss(o) for o in outs_c).backward()
+    sum(cases.scalar_loss(o) for o in outs_g).backward()
+    # one flipped silhouette pixel moves the summed depth by ~2.5 and the gradient accordingly
+    assert gu.rel(l_g.grad.cpu(), l_c.grad) < (2e-3 if flips == 0 else 3e-2)
