@@ -32,9 +32,9 @@ constexpr int NST = 6;                 // weight ring stages
 constexpr int STAGE_BYTES = 16384;     // per CTA: [hi 8 KB][lo 8 KB]
 constexpr int OFF_AHI = 0, OFF_ALO = 65536, OFF_W = 131072;
 constexpr int OFF_BAR = OFF_W + NST * STAGE_BYTES;   // 229376
-constexpr int OFF_PART = OFF_BAR + 256;              // per-row partial sums [64][8] (8 threads share a row)
+constexpr int OFF_PART = OFF_BAR + 512;              // per-row partial sums [64][8] (8 threads share a row)
 constexpr int OFF_ROWD = OFF_PART + 2048;            // per-row scalar [64]
-constexpr int SMEM_BYTES = OFF_ROWD + 256;           // 231936
+constexpr int SMEM_BYTES = OFF_ROWD + 256;           // 232192
 constexpr int NTHREADS = 640;                        // 4 service warps + 16 epilogue warps
 constexpr int MAX_PROG = 2 * 10;                     // forward + transposed chain, at most 10 tensor-core layers each
 
@@ -203,15 +203,17 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P, const 
   auto W_FULL = [&](int s) { return bar0 + 8 * s; };
   auto W_EMPTY = [&](int s) { return bar0 + 8 * (NST + s); };
   auto A_FULL = [&](int c) { return bar0 + 8 * (2 * NST + c); };
-  auto D_FULL = [&](int b) { return bar0 + 8 * (2 * NST + 16 + b); };
-  const uint32_t FIN = bar0 + 8 * (2 * NST + 18);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 8 * (2 * NST + 19));
+  auto A_FREE = [&](int c) { return bar0 + 8 * (2 * NST + 16 + c); };          // last read of A block c is complete
+  auto D_FULL = [&](int b, int h) { return bar0 + 8 * (2 * NST + 32 + 2 * b + h); };  // N-half h of buffer b complete
+  const uint32_t FIN = bar0 + 8 * (2 * NST + 36);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 8 * (2 * NST + 37));
   const int n_prog = P.n_prog;
 
   if (tid == 0) {
     for (int s = 0; s < NST; ++s) { mbar_init(W_FULL(s), 1); mbar_init(W_EMPTY(s), 1); }
     for (int c = 0; c < 16; ++c) mbar_init(A_FULL(c), 4);  // 2 warps x 2 CTAs produce each 32-feature block
-    mbar_init(D_FULL(0), 1); mbar_init(D_FULL(1), 1);
+    for (int c = 0; c < 16; ++c) mbar_init(A_FREE(c), 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(D_FULL(b, 0), 1); mbar_init(D_FULL(b, 1), 1); }
     mbar_init(FIN, 32);                                     // 16 epilogue warps x 2 CTAs
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -269,16 +271,21 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P, const 
           const uint32_t buf = G & 1;
           // the last accumulator of the previous tile lives in this buffer until its epilogue drained it
           if (m == 1 && !d_first) { mbar_wait_cluster(FIN, fin_phase); fin_phase ^= 1; }
-          for (int kc = 0; kc < kc32; ++kc) {
-            if (!(P.dbg & 2)) mbar_wait_cluster(A_FULL(kc), (a_phase >> kc) & 1);
-            a_phase ^= (1u << kc);
-            if ((P.dbg & 8) && io.dbg_out && cluster_id == 0 && t == cluster_id + n_clusters && lane == 0 && kc == 0) io.dbg_out[8 + m * 4 + 0] = clock64();
-            for (int h = 0; h < nh; ++h, ++it) {
+          // N-half outer, K block inner: half 0 of the accumulator completes while half 1 is still being computed, so
+          // its epilogue (the first A blocks of the next layer) overlaps the second pass.  A_FREE(kc) tells the epilogue
+          // when the last pass has consumed A block kc and its slot may be overwritten in place.
+          for (int h = 0; h < nh; ++h) {
+            const uint32_t d_addr = tmem + buf * 256 + h * 128;
+            for (int kc = 0; kc < kc32; ++kc, ++it) {
+              if (h == 0) {
+                if (!(P.dbg & 2)) mbar_wait_cluster(A_FULL(kc), (a_phase >> kc) & 1);
+                a_phase ^= (1u << kc);
+                if ((P.dbg & 8) && io.dbg_out && cluster_id == 0 && t == cluster_id + n_clusters && lane == 0 && kc == 0) io.dbg_out[8 + m * 4 + 0] = clock64();
+              }
               const int slot = it % NST;
               if (!(P.dbg & 1)) mbar_wait(W_FULL(slot), (it / NST) & 1);
               tc_fence_after();
               if (elect_one()) {
-                const uint32_t d_addr = tmem + buf * 256 + h * 128;
 #pragma unroll
                 for (int ks = 0; ks < 2; ++ks) {
                   const uint64_t a_off = (uint64_t)((kc * 4 + ks * 2) * 64);
@@ -288,7 +295,8 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P, const 
                   mma_f16_2cta(d_addr, a_hi0 + a_off, b_0 + b_off + 512, idesc, 1u);
                 }
                 commit_mc(W_EMPTY(slot));
-                if (kc == kc32 - 1 && h == nh - 1) commit_mc(D_FULL(buf));
+                if (h == nh - 1) commit_mc(A_FREE(kc));
+                if (kc == kc32 - 1) commit_mc(D_FULL(buf, h));
               }
               __syncwarp();
               if ((P.dbg & 8) && io.dbg_out && cluster_id == 0 && t == cluster_id + n_clusters && lane == 0 && kc == kc32 - 1 && h == nh - 1) io.dbg_out[8 + m * 4 + 1] = clock64();
@@ -311,7 +319,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P, const 
     float* part = reinterpret_cast<float*>(smem + OFF_PART);
     float* rowd = reinterpret_cast<float*>(smem + OFF_ROWD);
     const int pslot = 4 * q + ch;        // this thread's slot among the 8 threads that share a row
-    uint32_t G = 0, d_phase = 0;
+    uint32_t G = 0, d_phase = 0, free_phase = 0;
     float px = 0.f, py = 0.f, pz = 0.f;
     uint32_t mk[DIST_MAX_LAYERS][2];     // ReLU sign bits of this thread's (row, 32 features x 2 halves) per net layer
     float acc0r[2] = {0.f, 0.f}, acclr[2] = {0.f, 0.f};  // MODE 2: per-lane running column sums
@@ -389,11 +397,19 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P, const 
         const int LN = P.L[m].N, Lnh = P.L[m].nh, Lapp = P.L[m].app_xyz;
         const float cscale = P.L[m].inv_scale;
         const float* Lbias = P.L[m].bias;
-        mbar_wait(D_FULL(buf), (d_phase >> buf) & 1);
-        d_phase ^= (1u << buf);
-        tc_fence_after();
+        const int kc32_cur = P.L[m].kc32;
+        auto wait_half = [&](int h) {
+          const int bi = 2 * buf + h;
+          mbar_wait(D_FULL(buf, h), (d_phase >> bi) & 1);
+          d_phase ^= (1u << bi);
+          tc_fence_after();
+        };
+        // block kb of A may be overwritten once the last MMA pass of THIS layer has read it
+        auto wait_free = [&](int kb) {
+          if (kb < kc32_cur) mbar_wait(A_FREE(kb), (free_phase >> kb) & 1);
+        };
+        if (prog_last) for (int h = 0; h < Lnh; ++h) wait_half(h);   // all MMAs of the tile done before A is recycled
         const bool dbg_rec = (P.dbg & 8) && io.dbg_out && cluster_id == 0 && rank == 0 && warp == 4 && lane == 0 && t == cluster_id + n_clusters;
-        if (dbg_rec) io.dbg_out[8 + m * 4 + 2] = clock64();
         if (prog_last) {
           // all MMAs of this tile are complete: A is free -> start the next tile's layer 0 before draining D
           if (MODE != 0) { mk0s[0] = mk[0][0]; mk0s[1] = mk[0][1]; }
@@ -410,7 +426,9 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P, const 
           else if (fwd_last) { process = fb < LN; }
           else if (!prog_last) { need_store = kb < kblocks_next; process = need_store || (Lapp && fb < LN + 3 && fb + 32 > LN); }
           else { process = fb < LN + 3 * Lapp; }
+          if (!prog_last) wait_half(h);       // every epilogue warp waits for each half exactly once per layer
           if (!process) continue;
+          if (dbg_rec && h == 0) io.dbg_out[8 + m * 4 + 2] = clock64();
           float v[32];
           tmem_ld32(tmem + lane_base + buf * 256 + h * 128 + 32 * ch, v);
           const bool interior = (fb + 32 <= LN);            // warp-uniform: no per-element bounds checks
@@ -459,6 +477,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P, const 
                   if (fb + j < LN) dot = fmaf(v[j], __ldg(P.wlast + fb + j), dot);
               }
             } else if (need_store) {
+              wait_free(kb);
 #pragma unroll
               for (int g = 0; g < 4; ++g) store_group(smem, fb + 8 * g, row, &v[8 * g]);
               signal_block(kb);
@@ -505,6 +524,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P, const 
                 }
               }
             } else if (need_store) {
+              wait_free(kb);
 #pragma unroll
               for (int g = 0; g < 4; ++g) store_group(smem, fb + 8 * g, row, &v[8 * g]);
               signal_block(kb);
@@ -519,6 +539,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P, const 
           }
         }
         if (dbg_rec) io.dbg_out[8 + m * 4 + 3] = clock64();
+        free_phase ^= (kc32_cur >= 16) ? 0xFFFFu : ((1u << kc32_cur) - 1u);   // A_FREE(kb), kb < kc32, completed once this layer
         if (fwd_last) {
           // combine the 8 partial dot products of each row: bias, tanh (deep_sdf_decoder.py:109-110)
           part[row * 8 + pslot] = dot;

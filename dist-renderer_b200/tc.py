@@ -6,8 +6,8 @@ is issued as three fp16 tensor-core passes  A_hi*W_hi + A_lo*W_hi + A_hi*W_lo  w
 (the dropped lo*lo term is 2^-22 relative).  fp16 (11-bit significand) x 2 carries 22 bits -- the precision of the
 "TF32x2" row of SURVEY Table P -- at the fp16/bf16 MMA rate (2x the TF32 rate) and half the operand bytes.
 
-Blob layout (must match csrc/mlp_tc.cu): for each tensor-core layer, for each 32-wide K chunk kc, for each
-256-wide N half h, for each CTA r of the pair: a 16 KB stage = [hi 8 KB][lo 8 KB], each
+Blob layout (must match csrc/mlp_tc.cu): for each tensor-core layer, for each 256-wide N half h, for each 32-wide K
+chunk kc, for each CTA r of the pair: a 16 KB stage = [hi 8 KB][lo 8 KB], each
 [4 K-groups][128 n-rows][8 k] fp16 holding  W[n = 256 h + 128 r + row][k = 32 kc + 8 g + e] * sW  -- the no-swizzle
 K-major "panel" image the UMMA shared-memory descriptor reads (LBO = 2048 B between K-groups, SBO = 128 B between
 8-row groups), so one TMA box copy lands a stage without any reshuffling.
@@ -78,6 +78,7 @@ def _tiles(w, scale, c_trunc):
     def panels(t):  # [NH*256, Kp] -> [kc, NH, 2(r), 4(g), 128(row), 8(e)]
         return t.reshape(NH, 2, 128, kc, 4, 8).permute(3, 0, 1, 4, 2, 5)
     both = torch.stack([panels(hi), panels(lo)], 3)          # [kc, NH, r, hi/lo, g, row, e]
+    both = both.permute(1, 0, 2, 3, 4, 5, 6)                  # stage order of the kernel: N-half outer, K block inner
     return both.contiguous().reshape(-1), kc, NH
 
 
