@@ -37,7 +37,7 @@ class _DecodeFn(torch.autograd.Function):
     def forward(ctx, latent, points, plan, clamp_dist, engine):
         lib = _abi.lib()
         st = _stream()
-        net, _keep = plan.net_for(latent, engine, st)
+        net, engine, _keep = plan.net_for(latent, engine, st)
         pts = points.detach().float().contiguous()
         n = pts.shape[0]
         sdf = torch.empty(n, 1, device=pts.device, dtype=torch.float32)
@@ -53,14 +53,14 @@ class _DecodeFn(torch.autograd.Function):
     def backward(ctx, g):
         pts, latent = ctx.saved_tensors
         plan, lib, st = ctx.plan, _abi.lib(), _stream()
-        net, _keep = plan.net_for(latent if ctx.has_latent else None, ctx.engine, st)
+        net, eng_b, _keep = plan.net_for(latent if ctx.has_latent else None, ctx.engine, st)
         n = pts.shape[0]
         coef = g.detach().reshape(-1).float().contiguous()
         dpts = torch.zeros(n, 3, device=pts.device)
         acc0 = torch.zeros(plan.bias[0].numel(), device=pts.device)
         accl = torch.zeros(plan.bias[plan.latent_in].numel(), device=pts.device) if plan.latent_in >= 0 else None
         if n > 0:
-            _abi.check(lib.dist_decoder_backward(net, ctx.engine, _abi.ptr(pts), _abi.ptr(coef), None, n, None, ctx.cd,
+            _abi.check(lib.dist_decoder_backward(net, eng_b, _abi.ptr(pts), _abi.ptr(coef), None, n, None, ctx.cd,
                                                  _abi.ptr(dpts), _abi.ptr(acc0), _abi.ptr(accl), st))
         g_lat = plan.latent_grad(acc0, accl).reshape(latent.shape) if (ctx.has_latent and ctx.needs_input_grad[0]) \
             else None
@@ -96,7 +96,7 @@ def decode_sdf_gradient(decoder, latent_vector, points, clamp_dist=0.1, MAX_POIN
     plan = plan_for(decoder)
     eng = resolve_engine(plan, engine or DEFAULT_ENGINE)
     st = _stream()
-    net, _keep = plan.net_for(latent_vector, eng, st)
+    net, eng, _keep = plan.net_for(latent_vector, eng, st)
     pts = points.detach().float().contiguous()
     n = pts.shape[0]
     grad = torch.empty(n, 3, device=pts.device)

@@ -108,7 +108,8 @@ class DecoderPlan(object):
         if self.N[-1] != 1:
             raise NotImplementedError("last_dim != 1 decoders (colour) are not supported by the fused path")
         self.use_tanh = 1 if getattr(d, "use_tanh", False) else 0
-        self.tc = None      # tensor-core operand blobs, built lazily by tc_prepare()
+        self.tc = None      # tensor-core operand blobs, built lazily by tc.prepare()
+        self.tc_unsafe = False
         self._key = key
         return True
 
@@ -129,18 +130,23 @@ class DecoderPlan(object):
         return out0, outl, lat
 
     def net_for(self, latent, engine, stream):
-        """(dist_net_t, keepalive) for one call: prepares the tensor-core operands when that engine is selected,
+        """(dist_net_t, effective engine, keepalive) for one call: prepares the tensor-core operands when that engine is selected,
         folds the latent into the per-render biases and fills the descriptor."""
         if engine == _abi.ENGINE_TC:
             from . import tc
-            tc.prepare(self)
+            try:
+                tc.prepare(self)
+            except NotImplementedError:
+                if not getattr(self, "tc_unsafe", False):
+                    raise
+                engine = _abi.ENGINE_SIMT       # self-check failed (warned once): this call runs on the fp32 engine
         b0, bl, lat = self.fold(latent, stream)
         bl_tc = None
         if engine == _abi.ENGINE_TC and bl is not None:
             from . import tc
             bl_tc = bl * tc.S_ACT
         net = self.c_net(b0, bl, bl_tc)
-        return net, (b0, bl, bl_tc, lat)
+        return net, engine, (b0, bl, bl_tc, lat)
 
     def c_net(self, bias0, biasl, biasl_tc=None):
         """ctypes dist_net_t for one call; bias0/biasl are the folded biases (or None before folding)."""

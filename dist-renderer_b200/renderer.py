@@ -7,7 +7,7 @@ launches on the current stream and chains the tiny camera Jacobian (c = -R^T T, 
 
 Differences from the reference, all loud:
   * no CPU path: ``use_gpu=False`` or a CPU decoder raises;
-  * ``use_depth2normal``, ``num_forward_sampling`` and ``sample_index_type != 'min_abs'`` raise NotImplementedError;
+  * ``use_depth2normal`` and ``sample_index_type != 'min_abs'`` raise NotImplementedError;
     ``pyramid_recursive`` is implemented for the default ``scale_list=[4,2,1]`` on full images;
   * 3x4 ``transform_matrix`` raises (the reference's own 3x4 inverse path calls an un-imported ``pdb``);
   * when no ray meets the unit sphere the reference dies inside ``.max()`` of an empty tensor; here
@@ -41,7 +41,7 @@ class _RenderDepthFn(torch.autograd.Function):
         dev = ren.device
         P, B = ren.P, ren.buffer_size
         engine = resolve_engine(plan, opts["engine"])
-        net, _keep = plan.net_for(latent, engine, st)
+        net, engine, _keep = plan.net_for(latent, engine, st)
         Rd = R.detach().float().contiguous()
         cam_pos = torch.matmul(-Rd.t(), T.detach().float()[:, None]).squeeze(1).contiguous()  # renderer.py:186
         cam = ren._c_camera(Rd, cam_pos, opts["use_transform"])
@@ -83,7 +83,7 @@ class _RenderDepthFn(torch.autograd.Function):
         latent, Rd, Td = ctx.saved_tensors
         ren, opts, lib, st = ctx.ren, ctx.opts, _abi.lib(), _stream()
         plan, dev, P, B = ren.plan, ren.device, ren.P, ren.buffer_size
-        net, _keep = plan.net_for(latent, ctx.engine, st)
+        net, eng_b, _keep = plan.net_for(latent, ctx.engine, st)
         cam_pos = torch.matmul(-Rd.t(), Td[:, None]).squeeze(1).contiguous()
         cam = ren._c_camera(Rd, cam_pos, opts["use_transform"])
         scr = ren._scratch()
@@ -105,7 +105,7 @@ class _RenderDepthFn(torch.autograd.Function):
         g_lat = g_R = g_T = None
         if gZ is not None or gM is not None:
             s_row, s_pts, s_coef, s_dpts, s_cnt = scr["b_row"], scr["b_pts"], scr["b_coef"], scr["b_dpts"], scr["b_cnt"]
-            _abi.check(lib.dist_render_depth_bwd(net, ctx.engine, cam, ctx.mp, ws, _abi.ptr(gZ), _abi.ptr(gM),
+            _abi.check(lib.dist_render_depth_bwd(net, eng_b, cam, ctx.mp, ws, _abi.ptr(gZ), _abi.ptr(gM),
                                                  _abi.ptr(acc0), _abi.ptr(accl), _abi.ptr(d_cam), _abi.ptr(d_ray),
                                                  _abi.ptr(d_ray_c), _abi.ptr(s_row), _abi.ptr(s_pts), _abi.ptr(s_coef), None,
                                                  _abi.ptr(s_dpts), _abi.ptr(s_cnt), _abi.ptr(ren.rows_grad), st))
@@ -372,7 +372,7 @@ class SDFRenderer(object):
         plan = self.plan
         plan.refresh()
         engine = resolve_engine(plan, self.engine)
-        net, _keep = plan.net_for(latent, engine, st)
+        net, engine, _keep = plan.net_for(latent, engine, st)
         Rd = R.detach().float().contiguous()
         cam_pos = torch.matmul(-Rd.t(), T.detach().float()[:, None]).squeeze(1).contiguous()
         cam = self._c_camera(Rd, cam_pos, use_transform)
@@ -395,8 +395,6 @@ class SDFRenderer(object):
             no_grad_depth, no_grad_normal, no_grad_mask, no_grad_camera = True, True, True, True
         if self.use_depth2normal:
             raise NotImplementedError("use_depth2normal is outside the fused path")
-        if num_forward_sampling != 0:
-            raise NotImplementedError("num_forward_sampling is not implemented")
         h, w = self.local_hw
         Zdepth, valid_mask, min_abs_query = self.render_depth(
             latent, R, T, clamp_dist=clamp_dist, sample_index_type=sample_index_type, profile=profile, no_grad=no_grad,
@@ -409,8 +407,35 @@ class SDFRenderer(object):
         normal = torch.cat([normal[:1] * (-1), normal[1:]], 0)                   # renderer.py:979
         normal = normal.reshape(3, h, w).permute(1, 2, 0)
         out = (depth.reshape(h, w), normal, valid_mask.reshape(h, w).type(torch.uint8), min_abs_query.reshape(h, w))
+        if num_forward_sampling != 0:   # renderer.py:984-986
+            inside = self.forward_sampling(latent, R, T, Zdepth, valid_mask, clamp_dist=clamp_dist,
+                                           num_forward_sampling=num_forward_sampling, use_transform=use_transform)
+            out = out + (inside.reshape(h, w, num_forward_sampling),)
         self._raise_if_empty()   # deferred to here so that the whole render is enqueued before the host waits
         return out
+
+    def forward_sampling(self, latent, R, T, Zdepth, valid_mask, clamp_dist=0.1, num_forward_sampling=1, no_grad=False,
+                         use_transform=True):
+        """sdf + offset at points pushed `offset` beyond the hit point along the ray (renderer.py:912-941), (P, k).
+        The decoder rows go through decode_sdf (CUDA engines); differentiable w.r.t. latent and the camera."""
+        from .functional import decode_sdf
+        assert num_forward_sampling > 0
+        cam_pos = self.get_camera_location(R, T)
+        cam_rays = self.get_camera_rays(R)
+        inside = torch.zeros(self.P, num_forward_sampling, device=self.device, dtype=torch.float32)
+        valid_mask = valid_mask.bool()
+        idx = torch.nonzero(valid_mask).reshape(-1)
+        if idx.numel() == 0:
+            return inside
+        rays_v, z_v = cam_rays[:, idx], Zdepth[idx]
+        cols = []
+        for i in range(num_forward_sampling):
+            grid = 0.5 * clamp_dist * (i + 1) / num_forward_sampling
+            pts = self.generate_point_samples(cam_pos, rays_v, z_v + grid, has_zdepth_grad=False, inv_transform=use_transform)
+            sdf = decode_sdf(self.decoder, latent, pts.transpose(1, 0), clamp_dist=None, no_grad=no_grad,
+                             engine=self.engine).squeeze(-1)
+            cols.append(sdf[:, None] + grid)
+        return inside.index_copy(0, idx, torch.cat(cols, 1))
 
     def render_silhouette(self, latent, R, T, **kw):
         """(mask[h,w] uint8, min_abs_query[h,w]): the pair the reference uses as the silhouette (renderer.py:878,990)."""

@@ -25,7 +25,7 @@ S_GRAD = 256.0      # scale of the backward-chain operand (d sdf / d pre-activat
 
 def supported(plan):
     """True when the tcgen05 engine covers this decoder shape on this device."""
-    if not torch.cuda.is_available():
+    if not torch.cuda.is_available() or getattr(plan, "tc_unsafe", False):
         return False
     if _abi.lib().dist_device_supports_tc(plan.device.index if plan.device.index is not None else 0) != 1:
         return False
@@ -128,7 +128,34 @@ def prepare(plan):
         raise NotImplementedError("the tensor-core engine does not cover this decoder shape / device")
     c = calibrate(plan)
     plan.tc = _build(plan, c)
+    _self_check(plan)
     return plan.tc
+
+
+def _self_check(plan, n_points=4096, tol=2e-5):
+    """Guards the fp16 operand range: the split-fp16 engine must reproduce the exact-fp32 engine on a sample of this
+    decoder's own rows (activations beyond ~2000 or non-finite values would overflow the fp16 operands).  On failure
+    the plan is marked unsafe: 'auto' then resolves to the fp32 engine and engine='tc' raises."""
+    lib = _abi.lib()
+    st = torch.cuda.current_stream().cuda_stream
+    g = torch.Generator().manual_seed(4321)
+    pts = ((torch.rand(n_points, 3, generator=g) - 0.5) * 2.0).to(plan.device)
+    lat = (0.1 * torch.randn(plan.latent_size, generator=g)).to(plan.device) if plan.latent_size > 0 else None
+    b0, bl, _ = plan.fold(lat, st)
+    bl_tc = bl * S_ACT if bl is not None else None
+    ref = torch.empty(n_points, device=plan.device)
+    out = torch.empty(n_points, device=plan.device)
+    net = plan.c_net(b0, bl, bl_tc)
+    _abi.check(lib.dist_decoder_forward(net, _abi.ENGINE_SIMT, _abi.ptr(pts), n_points, None, 0.0, _abi.ptr(ref), st))
+    _abi.check(lib.dist_decoder_forward(net, _abi.ENGINE_TC, _abi.ptr(pts), n_points, None, 0.0, _abi.ptr(out), st))
+    err = float((out - ref).abs().max())
+    if not (err < tol):
+        import warnings
+        plan.tc = None
+        plan.tc_unsafe = True
+        warnings.warn("dist-renderer_b200: tensor-core engine disabled for this decoder (max |tc - fp32| = %g on a "
+                      "self-check sample: operand range exceeds fp16); using the fp32 engine" % err)
+        raise NotImplementedError("tensor-core engine failed its self-check for this decoder")
 
 
 def _build(plan, c_trunc):

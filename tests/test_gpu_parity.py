@@ -201,6 +201,29 @@ def test_row_band_sharding_equals_full():
             assert torch.equal(a, b[r::3])
 
 
+def test_forward_sampling_matches_reference_formula():
+    """render(num_forward_sampling=k): sdf + offset at points pushed inside along the ray (renderer.py:912-941),
+    checked against the oracle's decoder on the same points."""
+    from oracle.sdf_oracle import decode_sdf as o_decode
+    cs = cases.CASES["c1_recursive_64"]
+    dec_g, dec_c = gu.gpu_decoder("B"), cases.decoder("B")
+    K, R, T = cases.camera(cs["cam"], cs["hw"])
+    lat = cases.synth.make_latent()
+    ren = pkg.SDFRenderer(dec_g, K, img_hw=cs["hw"])
+    out = ren.render(lat.cuda(), R.cuda(), T.cuda(), ray_marching_type="recursive", no_grad=True, num_forward_sampling=3)
+    assert len(out) == 5 and out[4].shape == (64, 64, 3)
+    Z, m, _ = ren.render_depth(lat.cuda(), R.cuda(), T.cuda(), no_grad=True)
+    cam_pos = ren.get_camera_location(R.cuda(), T.cuda())
+    rays = ren.get_camera_rays(R.cuda())
+    for i in range(3):
+        grid = 0.5 * 0.1 * (i + 1) / 3
+        pts = ren.generate_point_samples(cam_pos, rays[:, m], Z[m] + grid).detach().t().cpu()
+        ref = o_decode(dec_c, lat, pts, clamp_dist=None).squeeze(-1).detach() + grid
+        got = out[4].reshape(-1, 3)[m.cpu(), i].cpu()
+        assert float((got - ref).abs().max()) < 5e-6
+    assert float(out[4].reshape(-1, 3)[~m.cpu()].abs().max()) == 0.0
+
+
 def test_api_errors():
     dec = gu.gpu_decoder("B")
     K, R, T = cases.camera(("front", 1.6), (16, 16))
@@ -209,7 +232,7 @@ def test_api_errors():
     with pytest.raises(NotImplementedError):
         pkg.SDFRenderer(dec, K, img_hw=(16, 16), scale_list=[2, 1], march_step_list=[3, -1]).render(lat, R.cuda(), T.cuda())
     with pytest.raises(NotImplementedError):
-        ren.render(lat, R.cuda(), T.cuda(), num_forward_sampling=2)
+        pkg.SDFRenderer(dec, K, img_hw=(16, 16), use_depth2normal=True).render(lat, R.cuda(), T.cuda())
     with pytest.raises(ValueError):
         ren.render_depth(lat, R.cuda(), T.cuda(), ray_marching_type="bogus")
     with pytest.raises(RuntimeError):
