@@ -77,7 +77,30 @@ class Decoder(nn.Module):
         return getattr(self, "lin%d" % l)
 
     def inference(self, input):
-        """Generic forward, rows = [latent | xyz] (deep_sdf_decoder.py:80-111).  Plain PyTorch."""
+        """Forward, rows = [latent | xyz] -> (K, 1)  (deep_sdf_decoder.py:80-111).
+
+        Under ``torch.no_grad()`` on a CUDA device, rows that all carry the SAME latent code (the layout decode_sdf
+        builds, decoder_utils.py:61-62) are evaluated by the fused CUDA engines; anything else (per-row latents,
+        gradients w.r.t. the weights, CPU tensors, unsupported specs) runs the generic PyTorch layers below."""
+        if (not torch.is_grad_enabled()) and input.is_cuda and input.dim() == 2 and input.shape[0] > 0 \
+                and input.shape[1] == self.latent_size + 3 and not self.training:
+            out = self._inference_fused(input)
+            if out is not None:
+                return out
+        return self._inference_torch(input)
+
+    def _inference_fused(self, input):
+        from .functional import decode_sdf
+        L = self.latent_size
+        lat = input[:1, :L]
+        if L > 0 and not bool((input[:, :L] == lat).all()):
+            return None
+        try:
+            return decode_sdf(self, lat if L > 0 else None, input[:, L:], clamp_dist=None, no_grad=True)
+        except NotImplementedError:
+            return None
+
+    def _inference_torch(self, input):
         xyz = input[:, -3:]
         x = input
         if input.shape[1] > 3 and self.latent_dropout:
@@ -99,7 +122,8 @@ class Decoder(nn.Module):
                     x = F.dropout(x, p=self.dropout_prob, training=self.training)
         return torch.tanh(x)
 
-    forward = inference
+    def forward(self, input):
+        return self.inference(input)
 
 
 def load_decoder(experiment_directory, checkpoint_num=None, parallel=False):

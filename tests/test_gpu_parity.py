@@ -224,6 +224,45 @@ def test_forward_sampling_matches_reference_formula():
     assert float(out[4].reshape(-1, 3)[~m.cpu()].abs().max()) == 0.0
 
 
+def test_tc_self_check_downgrades_out_of_range_decoder():
+    """Activations far beyond the fp16 operand range: the tensor-core self-check must trip, 'auto' must run on the
+    fp32 engine (same results as engine='simt'), and an explicit engine='tc' must raise."""
+    import copy
+    import warnings
+    dec = copy.deepcopy(cases.decoder("B"))
+    with torch.no_grad():
+        dec.lin1.weight_g.mul_(3e4)
+    dec = dec.cuda()
+    lat = cases.synth.make_latent().cuda()
+    pts = ((torch.rand(3000, 3) - 0.5) * 1.2).cuda()
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        a = pkg.decode_sdf(dec, lat, pts, clamp_dist=None)
+    assert any("tensor-core engine disabled" in str(x.message) for x in w)
+    b = pkg.decode_sdf(dec, lat, pts, clamp_dist=None, engine="simt")
+    assert torch.equal(a, b) and not bool(torch.isnan(a).any())
+    with pytest.raises(NotImplementedError):
+        pkg.decode_sdf(dec, lat, pts, clamp_dist=None, engine="tc")
+
+
+def test_decoder_inference_fused_path():
+    """Decoder.inference under no_grad with a shared latent runs on the fused engines and equals the torch layers."""
+    dec = gu.gpu_decoder("B")
+    lat = cases.synth.make_latent().cuda()
+    pts = ((torch.rand(5000, 3) - 0.5) * 1.2).cuda()
+    x = torch.cat([lat.expand(5000, -1), pts], 1)
+    ref = dec._inference_torch(x).detach()
+    n0 = cases.pkg._abi.lib().dist_launch_count() if hasattr(cases.pkg, "_abi") else None
+    with torch.no_grad():
+        got = dec.inference(x)
+    assert got.shape == (5000, 1) and float((got - ref).abs().max()) < 3e-6
+    x2 = x.clone()
+    x2[7, 0] += 0.5                                     # per-row latents: generic path, still correct
+    with torch.no_grad():
+        assert float((dec.inference(x2) - dec._inference_torch(x2)).abs().max()) == 0.0
+    assert dec.inference(x).grad_fn is not None         # grad mode: plain PyTorch graph (weights may be trained)
+
+
 def test_api_errors():
     dec = gu.gpu_decoder("B")
     K, R, T = cases.camera(("front", 1.6), (16, 16))
