@@ -32,7 +32,8 @@ class Net(C.Structure):
 
 
 class Camera(C.Structure):
-    _fields_ = [("Kinv", C.c_float * 9), ("M", C.c_float * 9), ("R", C.c_void_p), ("cam_pos", C.c_void_p),
+    _fields_ = [("Kinv", C.c_float * 9), ("M", C.c_float * 9), ("Mn", C.c_float * 9), ("R", C.c_void_p),
+                ("cam_pos", C.c_void_p),
                 ("width", C.c_int32), ("height", C.c_int32), ("row0", C.c_int32), ("row_step", C.c_int32),
                 ("n_rows", C.c_int32), ("radius", C.c_float)]
 

@@ -16,7 +16,7 @@ namespace dist {
 namespace {
 
 struct Cam {
-  float Kinv[9], M[9];
+  float Kinv[9], M[9], Mn[9];
   const float* R;
   const float* c;
   int W, H, row0, row_step, n_rows;
@@ -416,7 +416,7 @@ __global__ void k_normal_finish(Cam cam, const int32_t* idx_in, const float* gra
     }
 #pragma unroll
     for (int k = 0; k < 3; ++k)  // renderer.py:97 transform_matrix @ n
-      Znormal[(size_t)k * P + lp] = fmaf(cam.M[k * 3 + 2], g[2], fmaf(cam.M[k * 3 + 1], g[1], cam.M[k * 3] * g[0]));
+      Znormal[(size_t)k * P + lp] = fmaf(cam.Mn[k * 3 + 2], g[2], fmaf(cam.Mn[k * 3 + 1], g[1], cam.Mn[k * 3] * g[0]));
   }
 }
 
@@ -483,7 +483,7 @@ int make_cam(const dist_camera_t* cam, Cam* out) {
   DIST_REQUIRE(cam && cam->R && cam->cam_pos, "camera: null pointer");
   DIST_REQUIRE(cam->width > 0 && cam->n_rows > 0 && cam->row_step > 0, "camera: bad image/tile description");
   DIST_REQUIRE((int64_t)cam->width * cam->n_rows < (int64_t)(1u << 31) / DIST_MAX_BUFFER, "camera: tile too large");
-  for (int i = 0; i < 9; ++i) { out->Kinv[i] = cam->Kinv[i]; out->M[i] = cam->M[i]; }
+  for (int i = 0; i < 9; ++i) { out->Kinv[i] = cam->Kinv[i]; out->M[i] = cam->M[i]; out->Mn[i] = cam->Mn[i]; }
   out->R = cam->R; out->c = cam->cam_pos;
   out->W = cam->width; out->H = cam->height; out->row0 = cam->row0; out->row_step = cam->row_step;
   out->n_rows = cam->n_rows; out->radius = cam->radius;

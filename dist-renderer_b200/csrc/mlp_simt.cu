@@ -294,7 +294,10 @@ int mlp_simt_launch(const NetDev& net, int mode, const MlpArgs& a, cudaStream_t 
   DIST_REQUIRE(net.n_layers >= 2 && net.n_layers <= DIST_MAX_LAYERS, "mlp_simt: n_layers %d unsupported", net.n_layers);
   if (mode != 0) DIST_REQUIRE(net.n_layers - 1 <= MAXH_GRAD, "mlp_simt: at most %d hidden layers in gradient modes", MAXH_GRAD);
   if (a.n_host <= 0 && !a.n_dev) return DIST_OK;
-  static bool attr_done = false;
+  static bool attr_done_dev[64] = {false};
+  int cur_dev = 0;
+  cudaGetDevice(&cur_dev);
+  bool& attr_done = attr_done_dev[cur_dev & 63];
   if (!attr_done) {
     DIST_CHECK_CUDA(cudaFuncSetAttribute(mlp_simt_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemFwd));
     DIST_CHECK_CUDA(cudaFuncSetAttribute(mlp_simt_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemGrad));

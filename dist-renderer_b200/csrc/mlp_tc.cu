@@ -718,7 +718,10 @@ int mlp_tc_launch(const dist_net_t* net, const NetDev& nd, int mode, const MlpAr
                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)cr); return DIST_E_CUDA; }
 
-  static bool attr_done = false;
+  static bool attr_done_dev[64] = {false};
+  int cur_dev = 0;
+  cudaGetDevice(&cur_dev);
+  bool& attr_done = attr_done_dev[cur_dev & 63];
   if (!attr_done) {
     DIST_CHECK_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     DIST_CHECK_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));

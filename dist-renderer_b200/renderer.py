@@ -249,9 +249,10 @@ class SDFRenderer(object):
     def _c_camera(self, R, cam_pos, use_transform=True):
         cam = _abi.Camera()
         Kinv = np.linalg.inv(self.intrinsic).astype(np.float32).reshape(-1)
-        M = self.transform_matrix.detach().cpu().numpy().reshape(-1) if use_transform else np.eye(3).reshape(-1)
+        Mn = self.transform_matrix.detach().cpu().numpy().reshape(-1)
+        M = Mn if use_transform else np.eye(3).reshape(-1)
         for i in range(9):
-            cam.Kinv[i], cam.M[i] = float(Kinv[i]), float(M[i])
+            cam.Kinv[i], cam.M[i], cam.Mn[i] = float(Kinv[i]), float(M[i]), float(Mn[i])
         cam._keep = (R, cam_pos)
         cam.R, cam.cam_pos = R.data_ptr(), cam_pos.data_ptr()
         cam.width, cam.height = self.img_hw[1], self.img_hw[0]

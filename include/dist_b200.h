@@ -77,7 +77,9 @@ typedef struct dist_net {
 /* Camera + image description for one render (renderer.py:13-59,180-200). */
 typedef struct dist_camera {
   float Kinv[9];              /* inverse intrinsic, row-major (renderer.py:161-164) */
-  float M[9];                 /* transform_matrix, row-major (renderer.py:44-48); only 3x3 supported */
+  float M[9];                 /* matrix whose transpose maps world points into the decoder frame: transform_matrix
+                                 (renderer.py:44-48, :119), or identity when use_transform=False; only 3x3 supported */
+  float Mn[9];                /* transform_matrix applied to the normals (renderer.py:902) -- always the real one */
   const float* R;             /* device, [9] row-major world->camera rotation */
   const float* cam_pos;       /* device, [3]  = -R^T T  (renderer.py:180-188) */
   int32_t width;              /* full image width */

@@ -263,6 +263,22 @@ def test_decoder_inference_fused_path():
     assert dec.inference(x).grad_fn is not None         # grad mode: plain PyTorch graph (weights may be trained)
 
 
+def test_use_transform_false_and_custom_matrix():
+    """use_transform=False (points stay in the world frame, normals are still mapped by transform_matrix:
+    renderer.py:219-220 vs :902) and a non-default transform_matrix, vs the oracle."""
+    from oracle.sdf_oracle import OracleSDFRenderer
+    dec_c, dec_g = cases.decoder("B"), gu.gpu_decoder("B")
+    K, R, T = cases.camera(("lookat", 70.0, 35.0, 1.8, 1.1), (40, 40))
+    lat = cases.synth.make_latent()
+    Mrot = np.array([[0., 1., 0.], [0., 0., 1.], [1., 0., 0.]])
+    for tm, ut in ((None, False), (Mrot, True)):
+        ora = OracleSDFRenderer(dec_c, K, img_hw=(40, 40), transform_matrix=tm)
+        ren = pkg.SDFRenderer(dec_g, K, img_hw=(40, 40), transform_matrix=tm)
+        ref = ora.render(lat, R, T, ray_marching_type="recursive", no_grad=True, use_transform=ut)
+        out = ren.render(lat.cuda(), R.cuda(), T.cuda(), ray_marching_type="recursive", no_grad=True, use_transform=ut)
+        gu.compare([t.cpu() for t in out], [t.detach() for t in ref])
+
+
 def test_api_errors():
     dec = gu.gpu_decoder("B")
     K, R, T = cases.camera(("front", 1.6), (16, 16))
