@@ -33,28 +33,26 @@ class ShardedSDFRenderer(object):
 
 
 def pack_band(outs, max_rows, extra=None):
+    """[6, max_rows, W] fp32 (depth, normal xyz, mask, min_sdf; bands shorter than max_rows are zero padded) + extra."""
     depth, normal, mask, min_sdf = outs
     n_rows, W = depth.shape
-    buf = torch.zeros(6, max_rows, W, device=depth.device, dtype=torch.float32)
-    buf[0, :n_rows] = depth.detach()
-    buf[1:4, :n_rows] = normal.detach().permute(2, 0, 1)
-    buf[4, :n_rows] = mask.detach().float()
-    buf[5, :n_rows] = min_sdf.detach()
-    flat = buf.reshape(-1)
+    body = torch.cat([depth.detach()[None], normal.detach().permute(2, 0, 1), mask.detach().float()[None],
+                      min_sdf.detach()[None]], 0)
+    if n_rows < max_rows:
+        body = torch.cat([body, body.new_zeros(6, max_rows - n_rows, W)], 1)
+    flat = body.reshape(-1)
     if extra is not None:
         flat = torch.cat([flat, extra.detach().reshape(-1).float()])
     return flat
 
 
 def unpack_bands(gathered, img_hw, world, n_extra=0):
-    """gathered: [world, 6*max_rows*W + n_extra] -> full-image outputs (+ the per-rank extras [world, n_extra])."""
+    """gathered: [world, 6*max_rows*W + n_extra] -> full-image outputs (+ the per-rank extras [world, n_extra]).
+    Image row k*world + r is row k of rank r's band, so one permute interleaves all bands."""
     H, W = img_hw
     max_rows = (H + world - 1) // world
     body = gathered[:, :6 * max_rows * W].reshape(world, 6, max_rows, W)
-    full = torch.empty(6, H, W, device=gathered.device, dtype=torch.float32)
-    for r in range(world):
-        n = len(range(r, H, world))
-        full[:, r::world] = body[r, :, :n]
+    full = body.permute(1, 2, 0, 3).reshape(6, max_rows * world, W)[:, :H]
     extras = gathered[:, 6 * max_rows * W:] if n_extra else None
     return (full[0], full[1:4].permute(1, 2, 0), full[4].to(torch.uint8), full[5]), extras
 
