@@ -352,7 +352,12 @@ def main():
         roof = {"bound": "tensor", "achieved": achieved, "peak": peak_burst, "unit": "TFLOP/s",
                 "frac": achieved / peak_burst, "traffic": None, "peak_source": src + " dense bf16 (burst)",
                 "kernel": "decoder-row tile kernel, %d rows/launch, %.3f ms/launch" % (n_rows, k_ms),
-                "flop_per_row": F, "in_step_tflops": in_step, "in_step_frac_of_sustained": in_step / peak_sust,
+                "flop_per_row": F, "issued_tflops": (3 if ren.local.plan.tc is not None else 1) * achieved,
+                "issued_frac": (3 if ren.local.plan.tc is not None else 1) * achieved / peak_burst,
+                "note": "achieved counts USEFUL flops (F per folded decoder row); the tensor-core engine issues 3 fp16 "
+                        "MMA passes per logical GEMM (split-fp16 for fp32-level parity), see issued_*; ncu tensor-pipe "
+                        "activity is in profiles/r1_tc_summary.md",
+                "in_step_tflops": in_step, "in_step_frac_of_sustained": in_step / peak_sust,
                 "rows_fwd_per_step": rows_f / args.steps, "rows_grad_per_step": rows_g / args.steps}
         # ---- CPU baseline (oracle port) on a bounded sample, rank 0 at N=1 only
         if world == 1 and not args.no_cpu_baseline:

@@ -1,0 +1,100 @@
+"""SDFRenderer_warp -- two-view photometric warping on top of the CUDA sphere tracer.
+
+Drop-in for `core/sdfrenderer/renderer_warp.py:13-144`: view 1 is rendered with depth
+gradients, view 2 without; the hit points of view 1 are reprojected into view 2, filtered by a depth-consistency test
+against view 2's rendered depth, and the colours of both images are compared at the corresponding pixels (L1).
+All decoder work (two `render_depth` calls + one `render_normal`) runs on the engines of `renderer.SDFRenderer`;
+the reprojection / bilinear sampling is a handful of elementwise PyTorch ops on (3, N) tensors and stays in PyTorch,
+exactly as in the reference, so the loss carries gradients to `latent`, `R1`, `T1`.
+
+`grid_sample` is called with ``align_corners=True``: the reference was written for torch 1.1, whose default sampling
+convention that is; the pixel normalisation `2 x / (W - 1) - 1` of `loss_utils.py:19-21`
+only makes sense under it.
+"""
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from .renderer import SDFRenderer
+
+
+def grid_sample_on_img(img, xy):
+    """Bilinear sampling of img [B,C,H,W] at pixel coordinates xy [B,2,Ho,Wo]  (core/utils/loss_utils.py:9-25)."""
+    H, W = img.shape[2], img.shape[3]
+    gx = 2.0 * xy[:, 0] / max(W - 1, 1) - 1.0
+    gy = 2.0 * xy[:, 1] / max(H - 1, 1) - 1.0
+    return F.grid_sample(img, torch.stack([gx, gy], -1), align_corners=True)
+
+
+class SDFRenderer_warp(SDFRenderer):
+    def __init__(self, decoder, intrinsic, img_hw=None, march_step=50, buffer_size=5, ray_marching_ratio=1.5,
+                 max_sample_dist=0.2, threshold=5e-5, use_gpu=True, is_eval=True, transform_matrix=None, engine=None):
+        # renderer_warp.py:14-16
+        super(SDFRenderer_warp, self).__init__(decoder, intrinsic, img_hw=img_hw, transform_matrix=transform_matrix,
+                                               march_step=march_step, buffer_size=buffer_size,
+                                               ray_marching_ratio=ray_marching_ratio, max_sample_dist=max_sample_dist,
+                                               threshold=threshold, use_gpu=use_gpu, is_eval=is_eval, engine=engine)
+        self.counter = 0
+
+    # ------------------------------------------------------------------------------------------------------
+    def valid_points_depth(self, xy_proj, Zdepth2, depth2_proj, thres_depth):
+        """Squared difference between the reprojected depth and view 2's rendered depth (renderer_warp.py:62-72)."""
+        h, w = self.img_hw
+        depth2 = (Zdepth2 * self.calib_map).reshape(1, 1, h, w)
+        sampled = grid_sample_on_img(depth2, xy_proj).reshape(-1)
+        return (depth2_proj - sampled) ** 2 < thres_depth
+
+    def get_valid_points(self, render_out1, render_out2, R1, T1, R2, T2, thres_depth, gt_mask=None):
+        """renderer_warp.py:18-53: view-1 hit points (world frame, with depth gradient) projected into view 2."""
+        Zdepth1, valid_mask1, _ = render_out1
+        Zdepth2, _, _ = render_out2
+        cam_pos1 = self.get_camera_location(R1, T1)
+        rays1 = self.get_camera_rays(R1)[:, valid_mask1]
+        pts = self.generate_point_samples(cam_pos1, rays1, Zdepth1[valid_mask1], inv_transform=False,
+                                          has_zdepth_grad=True)
+        xyz = torch.matmul(self.K, torch.matmul(R2, pts) + T2[:, None])
+        xy = (xyz[:2, :] / xyz[2, :])[None, :, :, None]                      # [1, 2, N, 1]
+        keep_mask = torch.ones(xyz.shape[1], dtype=torch.bool, device=xyz.device)  # the mask test is disabled upstream (:43)
+        keep_depth = self.valid_points_depth(xy, Zdepth2, xyz[2, :], thres_depth)
+        return xy[:, :, keep_depth, :], keep_mask, keep_depth
+
+    def compute_loss_color(self, img1, img2, xy_proj, valid_mask1, valid_mask_index, valid_depth_index):
+        """Mean L1 colour difference at corresponding pixels + the two masked colour maps (renderer_warp.py:74-101)."""
+        h, w = self.img_hw
+        img1 = img1.to(self.device)
+        c1 = img1.reshape(h * w, 3)[valid_mask1][valid_mask_index][valid_depth_index]
+        c2 = grid_sample_on_img(img2.to(self.device).permute(2, 0, 1)[None], xy_proj)   # [1, 3, n, 1]
+        c2 = c2.reshape(3, -1).permute(1, 0)
+        loss = torch.mean(torch.abs(c1 - c2))
+        idx1 = torch.nonzero(valid_mask1).reshape(-1)[valid_mask_index][valid_depth_index]
+        final = torch.zeros(h * w, dtype=torch.bool, device=self.device)
+        final[idx1] = True
+        final = final.reshape(h, w)
+        vis1, vis2 = torch.zeros_like(img1), torch.zeros_like(img1)
+        vis1[final] = c1
+        vis2[final] = c2
+        return loss, vis1, vis2
+
+    def render_warp(self, latent, R1, T1, R2, T2, img1, img2, clamp_dist=0.1, profile=False, no_grad_normal=False,
+                    thres_depth=0.001):
+        """renderer_warp.py:103-144.  Returns (loss_color, color_valid_1, color_valid_2, valid_mask1, valid_mask2,
+        min_sdf_sample1, min_sdf_sample2, Znormal1, depth1_rendered)."""
+        h, w = self.img_hw
+        out1 = self.render_depth(latent, R1, T1, clamp_dist=clamp_dist, profile=profile)
+        out2 = self.render_depth(latent, R2, T2, clamp_dist=clamp_dist, profile=profile, no_grad_depth=True)
+        Zdepth1, valid_mask1, min_sdf1 = out1
+        Zdepth2, valid_mask2, min_sdf2 = out2
+        min_sdf1, min_sdf2 = min_sdf1.reshape(h, w), min_sdf2.reshape(h, w)
+        if int(valid_mask1.sum()) == 0:
+            loss_color = torch.zeros((), device=self.device, requires_grad=True)
+            vis1 = torch.zeros_like(img1).to(self.device)
+            vis2 = torch.zeros_like(img1).to(self.device)
+        else:
+            xy, km, kd = self.get_valid_points(out1, out2, R1, T1, R2, T2, thres_depth)
+            loss_color, vis1, vis2 = self.compute_loss_color(img1, img2, xy, valid_mask1, km, kd)
+        normal1 = self.render_normal(latent, R1, T1, Zdepth1, valid_mask1, no_grad=no_grad_normal, clamp_dist=clamp_dist)
+        Zn = torch.matmul(R1, normal1)
+        Zn = torch.cat([Zn[:1] * (-1), Zn[1:]], 0).reshape(3, h, w).permute(1, 2, 0)
+        depth1 = torch.where(valid_mask1, Zdepth1 * self.calib_map, torch.zeros_like(Zdepth1)).reshape(h, w)
+        return (loss_color, vis1, vis2, valid_mask1.reshape(h, w).type(torch.uint8),
+                valid_mask2.reshape(h, w).type(torch.uint8), min_sdf1, min_sdf2, Zn, depth1)

@@ -60,6 +60,18 @@ def main():
     np.savez_compressed(os.path.join(cases.GOLDEN_DIR, "decoder_points.npz"), points=pts.numpy(), sdf=sdf.numpy(),
                         grad=grad.numpy(), weights_checksum=cases.weights_checksum(dec))
     print("decoder_points", float(sdf.min()), float(sdf.max()))
+    # two-view warp fixture (reference SDFRenderer_warp.render_warp, core/sdfrenderer/renderer_warp.py:103)
+    Warp = ref_shim.load_warp()
+    hw, K, (R1, T1), (R2, T2), img1, img2 = cases.warp_case()
+    rw = Warp(ref, K, img_hw=hw, use_gpu=False)
+    lat = lat0.clone().requires_grad_(True)
+    out = rw.render_warp(lat, R1, T1, R2, T2, img1, img2)
+    out[0].backward()
+    np.savez_compressed(os.path.join(cases.GOLDEN_DIR, "warp_40.npz"), loss=float(out[0]), g_latent=lat.grad.numpy(),
+                        mask1=out[3].numpy(), mask2=out[4].numpy(), min_sdf1=out[5].detach().numpy(),
+                        normal1=out[7].detach().numpy(), depth1=out[8].detach().numpy(),
+                        weights_checksum=cases.weights_checksum(dec))
+    print("warp_40 loss", float(out[0]))
 
 
 if __name__ == "__main__":

@@ -32,7 +32,12 @@ _PATCH = {
         ("valid_mask[valid_mask] = valid_mask_render", "valid_mask[valid_mask.clone()] = valid_mask_render")],
     # loss_utils.py:43 -- uint8 mask only converted for cuda tensors
     "core/utils/loss_utils.py": [
-        ("img.type() == 'torch.cuda.ByteTensor'", "img.dtype == torch.uint8")],
+        ("img.type() == 'torch.cuda.ByteTensor'", "img.dtype == torch.uint8"),
+        # loss_utils.py:24 -- written for torch 1.1 whose grid_sample convention is align_corners=True
+        ("output = F.grid_sample(img, vgrid)", "output = F.grid_sample(img, vgrid, align_corners=True)")],
+    # renderer_warp.py:43 -- hard-coded .cuda()
+    "core/sdfrenderer/renderer_warp.py": [
+        ("torch.ones(xyz_proj.shape[1]).byte().cuda()", "torch.ones(xyz_proj.shape[1]).bool().to(xyz_proj.device)")],
 }
 
 _loaded = {}
@@ -61,6 +66,21 @@ def _load(mod, rel):
     sys.modules[mod] = m
     exec(compile(src, m.__file__, "exec"), m.__dict__)
     return m
+
+
+def load_warp():
+    """Returns the reference's SDFRenderer_warp class (core/sdfrenderer/renderer_warp.py), CPU-runnable."""
+    if "W" in _loaded:
+        return _loaded["W"]
+    R, _, _ = load()
+    sys.modules["renderer"] = R                      # renderer_warp.py:6 does `from renderer import SDFRenderer`
+    up = os.path.join(REF, "core", "utils")
+    if up not in sys.path:
+        sys.path.append(up)                          # loss_utils.py:7 `from pytorch_ssim import loss_ssim`
+    _load("core.utils.loss_utils", "core/utils/loss_utils.py")
+    W = _load("core.sdfrenderer.renderer_warp", "core/sdfrenderer/renderer_warp.py")
+    _loaded["W"] = W.SDFRenderer_warp
+    return _loaded["W"]
 
 
 def load():

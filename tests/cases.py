@@ -68,3 +68,13 @@ def scalar_loss(out):
 def weights_checksum(dec):
     with torch.no_grad():
         return float(sum(p.double().abs().sum() for p in dec.state_dict().values()))
+
+
+def warp_case():
+    """Two views 15 degrees apart on the ring + two seeded random images (config 4's origin: render_warp)."""
+    H = W = 40
+    K = synth.intrinsic(H, W, 1.2 * 2.5 / 1.6)
+    v1, v2 = synth.lookat_camera(20.0, 25.0, 2.5), synth.lookat_camera(35.0, 25.0, 2.5)
+    g = torch.Generator().manual_seed(9)
+    img1, img2 = torch.rand(H, W, 3, generator=g), torch.rand(H, W, 3, generator=g)
+    return (H, W), K, v1, v2, img1, img2

@@ -114,3 +114,27 @@ def test_multi_view_ring_gradients():
     sum(cases.scalar_loss(o) for o in outs_g).backward()
     # one flipped silhouette pixel moves the summed depth by ~2.5 and the gradient accordingly
     assert gu.rel(l_g.grad.cpu(), l_c.grad) < (2e-3 if flips == 0 else 3e-2)
+
+
+def test_render_warp_matches_oracle():
+    """next-1: SDFRenderer_warp.render_warp (two-view reprojection + photometric L1) vs the pinned CPU restatement."""
+    import importlib
+    import os
+    import numpy as np
+    from oracle.warp_oracle import OracleWarpRenderer
+    warp = importlib.import_module("dist-renderer_b200.renderer_warp")
+    hw, K, (R1, T1), (R2, T2), img1, img2 = cases.warp_case()
+    ow = OracleWarpRenderer(cases.decoder("B"), K, img_hw=hw)
+    l_c = synth.make_latent().requires_grad_(True)
+    ref = ow.render_warp(l_c, R1, T1, R2, T2, img1, img2)
+    ref[0].backward()
+    rw = warp.SDFRenderer_warp(gu.gpu_decoder("B"), K, img_hw=hw)
+    l_g = synth.make_latent().cuda().requires_grad_(True)
+    out = rw.render_warp(l_g, R1.cuda(), T1.cuda(), R2.cuda(), T2.cuda(), img1.cuda(), img2.cuda())
+    out[0].backward()
+    assert len(out) == 9 and out[1].shape == (40, 40, 3) and out[3].dtype == torch.uint8
+    assert int((out[3].cpu() != ref[1]).sum()) <= 2 and int((out[4].cpu() != ref[2]).sum()) <= 2
+    assert abs(float(out[0]) - float(ref[0])) < 2e-3 * abs(float(ref[0]))
+    assert gu.rel(l_g.grad.cpu(), l_c.grad) < 5e-2        # the depth-consistency test flips single correspondences
+    gold = np.load(os.path.join(cases.GOLDEN_DIR, "warp_40.npz"))
+    assert abs(float(out[0]) - float(gold["loss"])) < 2e-3 * float(gold["loss"])

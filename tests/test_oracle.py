@@ -96,3 +96,33 @@ def test_no_valid_depth_raises():
     ren = OracleSDFRenderer(dec, K, img_hw=(8, 8))
     with pytest.raises((ValueError, RuntimeError)):
         ren.render_depth(cases.synth.make_latent(), R, T, no_grad=True)
+
+
+def test_warp_oracle_matches_golden():
+    """oracle/warp_oracle.py vs the reference's render_warp outputs stored in tests/golden/warp_40.npz."""
+    from oracle.warp_oracle import OracleWarpRenderer
+    gold = np.load(os.path.join(cases.GOLDEN_DIR, "warp_40.npz"))
+    hw, K, (R1, T1), (R2, T2), img1, img2 = cases.warp_case()
+    ow = OracleWarpRenderer(cases.decoder("B"), K, img_hw=hw)
+    lat = cases.synth.make_latent().requires_grad_(True)
+    out = ow.render_warp(lat, R1, T1, R2, T2, img1, img2)
+    out[0].backward()
+    assert abs(float(out[0]) - float(gold["loss"])) < 1e-6
+    assert _rel(lat.grad.numpy(), gold["g_latent"]) < 1e-4
+    assert int((out[1].numpy() != gold["mask1"]).sum()) == 0 and int((out[2].numpy() != gold["mask2"]).sum()) == 0
+    assert _rel(out[6].detach().numpy(), gold["depth1"]) < 1e-6
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="reference tree not present (GPU box)")
+def test_warp_oracle_matches_live_reference():
+    from oracle.warp_oracle import OracleWarpRenderer
+    Warp = ref_shim.load_warp()
+    _, _, RefDecoder = ref_shim.load()
+    dec = cases.decoder("B")
+    ref = RefDecoder(dec.latent_size, **cases.synth.STANDARD_SPEC).eval()
+    ref.load_state_dict(dec.state_dict())
+    hw, K, (R1, T1), (R2, T2), img1, img2 = cases.warp_case()
+    a = Warp(ref, K, img_hw=hw, use_gpu=False).render_warp(cases.synth.make_latent(), R1, T1, R2, T2, img1, img2)
+    b = OracleWarpRenderer(dec, K, img_hw=hw).render_warp(cases.synth.make_latent(), R1, T1, R2, T2, img1, img2)
+    assert abs(float(a[0]) - float(b[0])) < 1e-7
+    assert _rel(b[5].detach(), a[7].detach()) < 1e-6
