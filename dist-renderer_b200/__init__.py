@@ -10,3 +10,4 @@ from .decoder import Decoder, load_decoder  # noqa: F401
 from .functional import decode_sdf, decode_sdf_gradient  # noqa: F401
 from .renderer import SDFRenderer  # noqa: F401
 from .renderer_warp import SDFRenderer_warp  # noqa: F401
+from . import evaluation  # noqa: F401

@@ -83,6 +83,28 @@ def load_warp():
     return _loaded["W"]
 
 
+def load_create_mesh():
+    """The reference's core/evaluation/create_mesh.py with skimage / plyfile stubbed (absent here; only the sampling
+    half is exercised), `.cuda()` / `.cpu()` round trips neutralised and the torch>=1.6 true-division of
+    create_mesh.py:23-24 restored to the integer division upstream DeepSDF intends."""
+    if "CM" in _loaded:
+        return _loaded["CM"]
+    _, DU, _ = load()
+    sk = types.ModuleType("skimage")
+    sk.measure = types.ModuleType("skimage.measure")
+    sys.modules.setdefault("skimage", sk)
+    sys.modules.setdefault("skimage.measure", sk.measure)
+    sys.modules.setdefault("plyfile", types.ModuleType("plyfile"))
+    sys.modules["decoder_utils"] = DU                 # create_mesh.py:8 `from decoder_utils import decode_sdf`
+    _PATCH["core/evaluation/create_mesh.py"] = [
+        ("samples[:, 1] = (overall_index.long() / N) % N", "samples[:, 1] = (overall_index.long() // N) % N"),
+        ("samples[:, 0] = ((overall_index.long() / N) / N) % N", "samples[:, 0] = ((overall_index.long() // N) // N) % N"),
+        ("0:3].cuda()", "0:3]"),
+    ]
+    _loaded["CM"] = _load("core.evaluation.create_mesh", "core/evaluation/create_mesh.py")
+    return _loaded["CM"]
+
+
 def load():
     """Returns (renderer_module, decoder_utils_module, DecoderClass) of the reference."""
     if _loaded:

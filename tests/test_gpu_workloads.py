@@ -138,3 +138,21 @@ def test_render_warp_matches_oracle():
     assert gu.rel(l_g.grad.cpu(), l_c.grad) < 5e-2        # the depth-consistency test flips single correspondences
     gold = np.load(os.path.join(cases.GOLDEN_DIR, "warp_40.npz"))
     assert abs(float(out[0]) - float(gold["loss"])) < 2e-3 * float(gold["loss"])
+
+
+def test_sdf_grid_matches_oracle():
+    """next-2: device-resident dense / coarse-to-fine SDF grid (create_mesh.py sampling half) vs the pinned oracle."""
+    import importlib
+    from oracle import grid_oracle
+    ev = importlib.import_module("dist-renderer_b200.evaluation")
+    dec_c, dec_g = cases.decoder("B"), gu.gpu_decoder("B")
+    lat = synth.make_latent()
+    N = 64          # 1.5 coarse voxels = 0.097 < the 0.1 clamp: the near/far classification is selective
+    ref, n_ref = grid_oracle.grid_speedup(dec_c, lat, N)
+    got, n_got = ev.sdf_grid_speedup(dec_g, lat.cuda(), N=N)
+    assert got.shape == (N, N, N) and abs(n_got - n_ref) <= 16 and 0 < n_got < N ** 3
+    d = (got.cpu() - ref).abs()
+    assert int((d > 1e-5).sum()) <= 16           # voxels whose coarse |sdf| sits on the near/far threshold (x8 children)
+    full = ev.sdf_grid(dec_g, lat.cuda(), N=32, transform=True)
+    pts = grid_oracle.get_samples(32, [-1, -1, -1], 2.0 / 31, True)
+    assert float((full.cpu().reshape(-1) - grid_oracle.infer(dec_c, lat, pts)).abs().max()) < 3e-6

@@ -126,3 +126,27 @@ def test_warp_oracle_matches_live_reference():
     b = OracleWarpRenderer(dec, K, img_hw=hw).render_warp(cases.synth.make_latent(), R1, T1, R2, T2, img1, img2)
     assert abs(float(a[0]) - float(b[0])) < 1e-7
     assert _rel(b[5].detach(), a[7].detach()) < 1e-6
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="reference tree not present (GPU box)")
+def test_grid_oracle_matches_live_reference():
+    """oracle/grid_oracle.py vs the reference's create_mesh.py sampling functions (next-2)."""
+    from oracle import grid_oracle
+    CM = ref_shim.load_create_mesh()
+    _, _, RefDecoder = ref_shim.load()
+    dec = cases.decoder("B")
+    ref = RefDecoder(dec.latent_size, **cases.synth.STANDARD_SPEC).eval()
+    ref.load_state_dict(dec.state_dict())
+    lat = cases.synth.make_latent()
+    N = 64          # 1.5 coarse voxels = 0.097 < the 0.1 clamp: the near/far classification becomes selective
+    vs, vsh = 2.0 / (N - 1), 2.0 / (N / 2 - 1)
+    assert torch.equal(CM.get_samples(N, [-1, -1, -1], vs, transform=True)[:, :3],
+                       grid_oracle.get_samples(N, [-1, -1, -1], vs, True))
+    sh = CM.get_samples(int(N / 2), [-1, -1, -1], vsh)
+    up = CM.upsample_cubic(CM.infer_samples(ref, lat, sh), int(N / 2), N)
+    pos, neg, val = CM.check_valid(up, vsh)
+    s = CM.get_samples(N, [-1, -1, -1], vs)
+    s[pos, 3], s[neg, 3] = 0.1, -0.1
+    s[val, 3] = CM.infer_samples(ref, lat, s[val, :])
+    og, n = grid_oracle.grid_speedup(dec, lat, N)
+    assert torch.equal(s[:, 3].reshape(N, N, N), og) and 0 < n < N ** 3
