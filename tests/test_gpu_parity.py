@@ -183,6 +183,30 @@ def test_small_generic_network():
     gu.compare(out, ref, g, gref)
 
 
+@pytest.mark.parametrize("shape", [dict(latent_size=64, width=256, depth=6, latent_in=3),
+                                   dict(latent_size=32, width=512, depth=4, latent_in=2),
+                                   dict(latent_size=128, width=384, depth=5, latent_in=None)])
+def test_tc_engine_other_network_shapes(shape):
+    """The tensor-core engine on non-standard DeepSDF shapes (other widths / depths / latent sizes / no latent_in)."""
+    import copy
+    dec_c = cases.synth.make_decoder("B", seed=11, **shape)
+    dec_g = copy.deepcopy(dec_c).cuda()
+    lat = cases.synth.make_latent(shape["latent_size"])
+    g = torch.Generator().manual_seed(12)
+    pts = ((torch.rand(20000, 3, generator=g) - 0.5) * 1.4)
+    a = pkg.decode_sdf(dec_g, lat.cuda(), pts.cuda(), clamp_dist=None, engine="simt")
+    b = pkg.decode_sdf(dec_g, lat.cuda(), pts.cuda(), clamp_dist=None, engine="tc")
+    assert float((a - b).abs().max()) < 3e-6
+    ga = pkg.decode_sdf_gradient(dec_g, lat.cuda(), pts.cuda(), engine="simt")
+    gb = pkg.decode_sdf_gradient(dec_g, lat.cuda(), pts.cuda(), engine="tc")
+    err = (ga - gb).norm(dim=1)
+    assert int((err > 1e-3).sum()) <= 10 and gu.rel(gb[err <= 1e-3], ga[err <= 1e-3]) < 5e-6
+    cs = dict(decoder=None, hw=(24, 24), cam=("front", 1.6), march_step=30, buffer_size=3, kind="pyramid_recursive")
+    out, gr, _ = gu.run_gpu(cs, engine="tc", dec=dec_g)
+    ref, gref = gu.run_oracle(cs, dec=dec_c)
+    gu.compare(out, ref, gr, gref)
+
+
 def test_row_band_sharding_equals_full():
     """Rendering interleaved row bands (multi-GPU ray-tile sharding) reproduces the full image exactly."""
     cs = cases.CASES["ragged_37x53"]
