@@ -5,18 +5,26 @@
 //   * layer 0 (K = 3, xyz) and the last layer (N = 1, dot product + tanh) run on CUDA cores in the epilogue warps;
 //   * every hidden layer is a tcgen05.mma.cta_group::2.kind::f16 GEMM (M = 128 over the pair, N = 256 per instruction,
 //     K = 16) with split-fp16 operands: D += A_hi*W_hi + A_lo*W_hi + A_hi*W_lo, fp32 accumulation in TMEM
-//     (see tc.py for the precision argument);
+//     (see tc.py for the precision argument and the truncation pre-compensation);
 //   * A (activations, 64 rows x K x {hi,lo} fp16 = 128 KB) is resident in shared memory in the UMMA no-swizzle
 //     K-major "panel" layout and is rewritten in place by the epilogue of each layer (TMEM -> registers -> bias,
 //     ReLU, split -> smem); it never touches HBM;
 //   * W streams L2 -> smem through a 6-stage ring of 16 KB TMA box copies per CTA (each CTA holds half of the
 //     256 N-rows of a stage; `.cta_group::2` copies signal the leader CTA's mbarrier), released by tcgen05.commit;
-//   * accumulators ping-pong between two 256-column TMEM buffers so the epilogue of layer l overlaps the MMAs of
-//     layer l+1 chunk by chunk (per-64-feature `a_full` barriers).
+//   * the MMA order is N-half outer / K block inner: accumulator half 0 (128 TMEM columns) completes while half 1 is
+//     still being computed, so its epilogue -- which produces the first eight 32-feature A blocks of the NEXT layer --
+//     overlaps the second pass; an A block is overwritten in place only after the last pass has read it (A_FREE
+//     barriers committed by the MMA issuer), and the next layer starts on block 0 the moment the current one ends;
+//   * accumulators ping-pong between two 256-column TMEM buffers; 16 epilogue warps own 32 rows x 32 columns each;
+//   * the transposed chain (input gradient / backward replay) is the same machinery on W^T tiles, with the ReLU sign
+//     bits kept per thread and the latent gradient accumulated as per-lane running column sums.
 // Warp roles per CTA (640 threads): warp 0 TMA producer, warp 1 MMA issuer (leader CTA), warp 2 TMEM allocator,
 // warps 4-19 epilogue (TMEM lane quarter = warp % 4, 32-column quarter = (warp-4)/4).
+// DIST_TC_DEBUG (env): bit 2 prints cycles/ns of CTA 0, bit 3 adds a per-layer timeline, bit 0 skips the weight waits
+// (timing experiments only; results are garbage with bit 0).
 //
-// Replaces: Decoder.inference / decode_sdf (core/graph/deep_sdf_decoder.py:80-111, core/utils/decoder_utils.py:53-74)
+// Replaces: Decoder.inference / decode_sdf / decode_sdf_gradient and the autograd backward through them
+// (core/graph/deep_sdf_decoder.py:80-111, core/utils/decoder_utils.py:53-92)
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -64,7 +72,7 @@ struct TcParams {
   int use_tanh;
   float sA, sD;                    // activation / gradient operand scales
   int first_append;                // layer 0's output gets xyz appended (latent_in == 1)
-  int dbg;                         // timing experiments only (DIST_TC_DEBUG): bit0 skip W_FULL waits, bit1 skip A_FULL waits
+  int dbg;                         // diagnostics (DIST_TC_DEBUG), see the file header
 };
 
 struct TcIO {
@@ -145,25 +153,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-__device__ __forceinline__ void tmem_ld64(uint32_t taddr, float (&v)[64]) {
-  uint32_t r[64];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x64.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,"
-      "%23,%24,%25,%26,%27,%28,%29,%30,%31,%32,%33,%34,%35,%36,%37,%38,%39,%40,%41,%42,%43,%44,%45,%46,%47,%48,%49,%50,%51,%52,"
-      "%53,%54,%55,%56,%57,%58,%59,%60,%61,%62,%63}, [%64];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]), "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]),
-        "=r"(r[37]), "=r"(r[38]), "=r"(r[39]), "=r"(r[40]), "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]),
-        "=r"(r[46]), "=r"(r[47]), "=r"(r[48]), "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]),
-        "=r"(r[55]), "=r"(r[56]), "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(r[i]);
 }
 
 // Writes 8 consecutive features (one K-group panel row) of this thread's row: x[] already multiplied by sA.
@@ -278,7 +267,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P, const 
             const uint32_t d_addr = tmem + buf * 256 + h * 128;
             for (int kc = 0; kc < kc32; ++kc, ++it) {
               if (h == 0) {
-                if (!(P.dbg & 2)) mbar_wait_cluster(A_FULL(kc), (a_phase >> kc) & 1);
+                mbar_wait_cluster(A_FULL(kc), (a_phase >> kc) & 1);
                 a_phase ^= (1u << kc);
                 if ((P.dbg & 8) && io.dbg_out && cluster_id == 0 && t == cluster_id + n_clusters && lane == 0 && kc == 0) io.dbg_out[8 + m * 4 + 0] = clock64();
               }

@@ -35,7 +35,7 @@ def supported(plan):
     if plan.K[0] != 3:
         return False
     for l in range(n - 1):
-        if plan.N[l] > 512:
+        if plan.N[l] > 512 or plan.K[l + 1] > 512:      # A buffer / barrier sets cover 16 blocks of 32 features
             return False
         app = 3 if (l + 1 == plan.latent_in) else 0
         if plan.N[l] + app > 256 * ((plan.N[l] + 255) // 256):

@@ -113,7 +113,7 @@ typedef struct dist_workspace {
   float* exit_;      /* [P] entry + chord (renderer.py:275-282) */
   float* dist;       /* [P] distance of the ray to the origin */
   float* z;          /* [P] marching depth relative to entry */
-  uint8_t* flags;    /* [P] bit0 sphere hit, bit1 first query > threshold, bit2 was live in the last executed step */
+  uint8_t* flags;    /* [P] bit0 sphere hit, bit1 first query > threshold */
   int32_t* nreal;    /* [P] number of real samples recorded */
   float* top_sdf;    /* [B][P] samples with the smallest |sdf|, sorted ascending */
   float* top_pt;     /* [B][3][P] their points (decoder frame) */
