@@ -20,8 +20,7 @@
 //     bits kept per thread and the latent gradient accumulated as per-lane running column sums.
 // Warp roles per CTA (640 threads): warp 0 TMA producer, warp 1 MMA issuer (leader CTA), warp 2 TMEM allocator,
 // warps 4-19 epilogue (TMEM lane quarter = warp % 4, 32-column quarter = (warp-4)/4).
-// DIST_TC_DEBUG (env): bit 2 prints cycles/ns of CTA 0, bit 3 adds a per-layer timeline, bit 0 skips the weight waits
-// (timing experiments only; results are garbage with bit 0).
+// DIST_TC_DEBUG (env): bit 2 prints cycles/ns of CTA 0 (+ a per-layer timeline when compiled with -DDIST_TC_TIMELINE).
 //
 // Replaces: Decoder.inference / decode_sdf / decode_sdf_gradient and the autograd backward through them
 // (core/graph/deep_sdf_decoder.py:80-111, core/utils/decoder_utils.py:53-92)
@@ -221,14 +220,14 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P, const 
     // the whole warp runs the loop (warp-uniform control flow keeps addresses in uniform registers); one elected
     // lane issues the copies
     {
-      uint32_t it = 0;
+      uint32_t p_slot = 0, p_phase = 0;
       const uint32_t bar_leader_mask = 0xFEFFFFFFu;
       for (int64_t t = cluster_id; t < n_tiles; t += n_clusters) {
         for (int m = 0; m < n_prog; ++m) {
           const int nstage = P.L[m].kc32 * P.L[m].nh, sb = P.L[m].stage_base;
-          for (int s = 0; s < nstage; ++s, ++it) {
-            const int slot = it % NST;
-            const uint32_t ph = (it / NST) & 1;
+          for (int s = 0; s < nstage; ++s) {
+            const uint32_t slot = p_slot, ph = p_phase;
+            if (++p_slot == NST) { p_slot = 0; p_phase ^= 1; }
             mbar_wait(W_EMPTY(slot), ph ^ 1);
             if (elect_one()) {
               if (rank == 0) mbar_expect_tx(W_FULL(slot), 2 * STAGE_BYTES);
@@ -252,7 +251,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P, const 
       const uint64_t a_hi0 = make_desc(sbase + OFF_AHI, 1024, 128);
       const uint64_t a_lo0 = make_desc(sbase + OFF_ALO, 1024, 128);
       const uint64_t b_0 = make_desc(sbase + OFF_W, 2048, 128);
-      uint32_t it = 0, G = 0, a_phase = 0, fin_phase = 0;
+      uint32_t G = 0, a_phase = 0, fin_phase = 0, w_slot = 0, w_phase = 0;
       uint32_t d_first = 1;
       for (int64_t t = cluster_id; t < n_tiles; t += n_clusters) {
         for (int m = 0; m < n_prog; ++m, ++G) {
@@ -263,32 +262,50 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P, const 
           // N-half outer, K block inner: half 0 of the accumulator completes while half 1 is still being computed, so
           // its epilogue (the first A blocks of the next layer) overlaps the second pass.  A_FREE(kc) tells the epilogue
           // when the last pass has consumed A block kc and its slot may be overwritten in place.
+          // The issuing thread is the bottleneck of this kernel (6 MMAs = 384 tensor cycles per stage): two stages are
+          // issued per barrier round trip, ring slot / phase are tracked incrementally, nothing else is in the loop.
           for (int h = 0; h < nh; ++h) {
             const uint32_t d_addr = tmem + buf * 256 + h * 128;
-            for (int kc = 0; kc < kc32; ++kc, ++it) {
+            const bool last_pass = (h == nh - 1);
+            for (int kc = 0; kc < kc32; kc += 2) {
               if (h == 0) {
                 mbar_wait_cluster(A_FULL(kc), (a_phase >> kc) & 1);
-                a_phase ^= (1u << kc);
-                if ((P.dbg & 8) && io.dbg_out && cluster_id == 0 && t == cluster_id + n_clusters && lane == 0 && kc == 0) io.dbg_out[8 + m * 4 + 0] = clock64();
+                mbar_wait_cluster(A_FULL(kc + 1), (a_phase >> (kc + 1)) & 1);
+                a_phase ^= (3u << kc);
+#ifdef DIST_TC_TIMELINE
+                if (io.dbg_out && cluster_id == 0 && t == cluster_id + n_clusters && lane == 0 && kc == 0) io.dbg_out[8 + m * 4 + 0] = clock64();
+#endif
               }
-              const int slot = it % NST;
-              if (!(P.dbg & 1)) mbar_wait(W_FULL(slot), (it / NST) & 1);
+              const uint32_t slot0 = w_slot, ph0 = w_phase;
+              uint32_t slot1 = slot0 + 1, ph1 = ph0;
+              if (slot1 == NST) { slot1 = 0; ph1 ^= 1; }
+              w_slot = slot1 + 1; w_phase = ph1;
+              if (w_slot == NST) { w_slot = 0; w_phase ^= 1; }
+              mbar_wait(W_FULL(slot0), ph0);
+              mbar_wait(W_FULL(slot1), ph1);
               tc_fence_after();
               if (elect_one()) {
 #pragma unroll
-                for (int ks = 0; ks < 2; ++ks) {
-                  const uint64_t a_off = (uint64_t)((kc * 4 + ks * 2) * 64);
-                  const uint64_t b_off = (uint64_t)(slot * (STAGE_BYTES / 16) + ks * 256);
-                  mma_f16_2cta(d_addr, a_hi0 + a_off, b_0 + b_off, idesc, (kc | ks) ? 1u : 0u);
-                  mma_f16_2cta(d_addr, a_lo0 + a_off, b_0 + b_off, idesc, 1u);
-                  mma_f16_2cta(d_addr, a_hi0 + a_off, b_0 + b_off + 512, idesc, 1u);
+                for (int u = 0; u < 2; ++u) {
+                  const uint32_t slot = u ? slot1 : slot0;
+#pragma unroll
+                  for (int ks = 0; ks < 2; ++ks) {
+                    const uint64_t a_off = (uint64_t)(((kc + u) * 4 + ks * 2) * 64);
+                    const uint64_t b_off = (uint64_t)(slot * (STAGE_BYTES / 16) + ks * 256);
+                    mma_f16_2cta(d_addr, a_hi0 + a_off, b_0 + b_off, idesc, ((kc + u) | ks) ? 1u : 0u);
+                    mma_f16_2cta(d_addr, a_lo0 + a_off, b_0 + b_off, idesc, 1u);
+                    mma_f16_2cta(d_addr, a_hi0 + a_off, b_0 + b_off + 512, idesc, 1u);
+                  }
+                  commit_mc(W_EMPTY(slot));
+                  if (last_pass) commit_mc(A_FREE(kc + u));
                 }
-                commit_mc(W_EMPTY(slot));
-                if (h == nh - 1) commit_mc(A_FREE(kc));
-                if (kc == kc32 - 1) commit_mc(D_FULL(buf, h));
+                if (kc + 2 >= kc32) commit_mc(D_FULL(buf, h));
               }
               __syncwarp();
-              if ((P.dbg & 8) && io.dbg_out && cluster_id == 0 && t == cluster_id + n_clusters && lane == 0 && kc == kc32 - 1 && h == nh - 1) io.dbg_out[8 + m * 4 + 1] = clock64();
+#ifdef DIST_TC_TIMELINE
+              if (io.dbg_out && cluster_id == 0 && t == cluster_id + n_clusters && lane == 0 && kc + 2 >= kc32 && last_pass) io.dbg_out[8 + m * 4 + 1] = clock64();
+              if (io.dbg_out && cluster_id == 0 && t == cluster_id && lane == 0 && kc + 2 >= kc32 && last_pass && m == n_prog - 1) io.dbg_out[200] = clock64();
+#endif
             }
           }
         }
@@ -397,12 +414,19 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P, const 
         auto wait_free = [&](int kb) {
           if (kb < kc32_cur) mbar_wait(A_FREE(kb), (free_phase >> kb) & 1);
         };
+        // the next tile's points are fetched before the wait so that their latency hides behind the last MMAs
+        // (px/py/pz of this tile are no longer needed: xyz is only appended in earlier forward layers)
+        if (prog_last && t + n_clusters < n_tiles) load_point(t + n_clusters);
         if (prog_last) for (int h = 0; h < Lnh; ++h) wait_half(h);   // all MMAs of the tile done before A is recycled
-        const bool dbg_rec = (P.dbg & 8) && io.dbg_out && cluster_id == 0 && rank == 0 && warp == 4 && lane == 0 && t == cluster_id + n_clusters;
+#ifdef DIST_TC_TIMELINE
+        const bool dbg_rec = io.dbg_out && cluster_id == 0 && rank == 0 && warp == 4 && lane == 0 && t == cluster_id + n_clusters;
+#else
+        const bool dbg_rec = false;
+#endif
         if (prog_last) {
           // all MMAs of this tile are complete: A is free -> start the next tile's layer 0 before draining D
           if (MODE != 0) { mk0s[0] = mk[0][0]; mk0s[1] = mk[0][1]; }
-          if (t + n_clusters < n_tiles) { load_point(t + n_clusters); layer0(); }
+          if (t + n_clusters < n_tiles) layer0();
         }
         const int kblocks_next = prog_last ? 0 : P.L[m + 1].kc32;
         // net layer whose ReLU mask gates the values produced here (transposed chain): l-1 with l = 2 n_mma - m
@@ -731,14 +755,17 @@ int mlp_tc_launch(const dist_net_t* net, const NetDev& nd, int mode, const MlpAr
     cudaStreamSynchronize(stream);
     cudaMemcpy(h, dbg_buf, 16, cudaMemcpyDeviceToHost);
     fprintf(stderr, "[tc dbg] mode %d: %lld cycles, %lld ns -> %.3f GHz\n", mode, h[0], h[1], h[1] ? (double)h[0] / h[1] : 0.0);
-    if (P.dbg & 8) {
+#ifdef DIST_TC_TIMELINE
+    {
       long long ev[256];
       cudaMemcpy(ev, dbg_buf, 2048, cudaMemcpyDeviceToHost);
       const long long t0 = ev[8];
+      fprintf(stderr, "[tc dbg] previous tile: last MMA issue at %lld (relative to this tile's first MMA)\n", ev[200] - t0);
       for (int m = 0; m < P.n_prog; ++m)
         fprintf(stderr, "[tc dbg] layer %2d: mma start %7lld  issue end %7lld | epi start %7lld  epi end %7lld\n", m, ev[8 + m * 4] - t0,
                 ev[8 + m * 4 + 1] - t0, ev[8 + m * 4 + 2] - t0, ev[8 + m * 4 + 3] - t0);
     }
+#endif
   }
   return DIST_OK;
 }
