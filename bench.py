@@ -206,6 +206,21 @@ def config_of(n_gpus, side):
             "l2": "flushed between timed iterations (256 MiB write)"}
 
 
+def ncu_traffic(tc):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel on the same 262,144-row batch,
+    from the committed `ncu --set full` capture (profiles/r1_*_raw.csv); None when no capture is committed."""
+    import csv
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles",
+                        "r1_tc_fwd_raw.csv" if tc else "r1_simt_fwd_raw.csv")
+    try:
+        rows = list(csv.reader(open(path)))
+        unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        col = {h: i for i, h in enumerate(rows[0])}
+        return sum(float(rows[2][col[k]]) * unit[rows[1][col[k]]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+    except Exception:
+        return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -341,6 +356,7 @@ def main():
             pkg.decode_sdf(dec, lat_d, pts, clamp_dist=None, no_grad=True, engine=args.engine)
         reps = 5
         torch.cuda.synchronize()
+        time.sleep(1.5)     # "timed alone": let the power-capped clocks of the long timed loops above recover
         e0.record()
         for _ in range(reps):
             pkg.decode_sdf(dec, lat_d, pts, clamp_dist=None, no_grad=True, engine=args.engine)
@@ -350,7 +366,7 @@ def main():
         achieved = n_rows * F / (k_ms * 1e-3) / 1e12
         in_step = (rows_f * F + rows_g * 2 * F) / (ms * 1e-3) / 1e12
         roof = {"bound": "tensor", "achieved": achieved, "peak": peak_burst, "unit": "TFLOP/s",
-                "frac": achieved / peak_burst, "traffic": None, "peak_source": src + " dense bf16 (burst)",
+                "frac": achieved / peak_burst, "traffic": ncu_traffic(ren.local.plan.tc is not None), "peak_source": src + " dense bf16 (burst)",
                 "kernel": "decoder-row tile kernel, %d rows/launch, %.3f ms/launch" % (n_rows, k_ms),
                 "flop_per_row": F, "issued_tflops": (3 if ren.local.plan.tc is not None else 1) * achieved,
                 "issued_frac": (3 if ren.local.plan.tc is not None else 1) * achieved / peak_burst,
