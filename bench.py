@@ -222,6 +222,8 @@ def ncu_traffic(tc):
 
 
 def main():
+    # NCCL writes its version / INFO lines to stdout by default; stdout carries exactly one JSON line
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
