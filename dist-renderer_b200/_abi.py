@@ -57,6 +57,8 @@ PROTOTYPES = {
     "dist_abi_version": (C.c_int, []),
     "dist_last_error": (C.c_char_p, []),
     "dist_launch_count": (C.c_longlong, []),
+    "dist_profile_begin": (C.c_int, []),
+    "dist_profile_end": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "dist_device_supports_tc": (C.c_int, [C.c_int]),
     "dist_fold_latent": (C.c_int, [C.POINTER(Net), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dist_decoder_forward": (C.c_int, [C.POINTER(Net), C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_float,

@@ -4,6 +4,7 @@
 #include <atomic>
 #include <stdio.h>
 #include <string.h>
+#include <vector>
 #include "common.cuh"
 
 namespace dist {
@@ -26,6 +27,30 @@ int num_sms() {
   int& n = cache[dev & 63];
   if (n == 0 && (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)) n = 148;
   return n;
+}
+
+// ---- optional event timing of the decoder-row kernels (dist_profile_begin / dist_profile_end)
+static bool g_prof_on = false;
+static std::vector<cudaEvent_t> g_prof_pool;   // events are created once and reused across windows
+static size_t g_prof_used = 0;
+static const size_t kProfMaxEvents = 2 * 65536;
+
+int mlp_launch(const dist_net_t* net, const NetDev& nd, int engine, int mode, const MlpArgs& a, cudaStream_t stream) {
+  const bool timed = g_prof_on && g_prof_used + 2 <= kProfMaxEvents;
+  if (timed) {
+    while (g_prof_pool.size() < g_prof_used + 2) {
+      cudaEvent_t e;
+      DIST_CHECK_CUDA(cudaEventCreate(&e));
+      g_prof_pool.push_back(e);
+    }
+    DIST_CHECK_CUDA(cudaEventRecord(g_prof_pool[g_prof_used], stream));
+  }
+  const int rc = (engine == DIST_ENGINE_TC) ? mlp_tc_launch(net, nd, mode, a, stream) : mlp_simt_launch(nd, mode, a, stream);
+  if (timed) {
+    DIST_CHECK_CUDA(cudaEventRecord(g_prof_pool[g_prof_used + 1], stream));
+    g_prof_used += 2;
+  }
+  return rc;
 }
 
 int make_netdev(const dist_net_t* net, NetDev* out) {
@@ -80,6 +105,27 @@ extern "C" {
 int dist_abi_version(void) { return DIST_ABI_VERSION; }
 const char* dist_last_error(void) { return g_err; }
 long long dist_launch_count(void) { return g_launches.load(); }
+
+int dist_profile_begin(void) {
+  g_prof_used = 0;
+  g_prof_on = true;
+  return DIST_OK;
+}
+
+int dist_profile_end(double* total_ms, long long* launches) {
+  g_prof_on = false;
+  double sum = 0.0;
+  for (size_t i = 0; i + 1 < g_prof_used; i += 2) {
+    DIST_CHECK_CUDA(cudaEventSynchronize(g_prof_pool[i + 1]));
+    float ms = 0.f;
+    DIST_CHECK_CUDA(cudaEventElapsedTime(&ms, g_prof_pool[i], g_prof_pool[i + 1]));
+    sum += ms;
+  }
+  if (total_ms) *total_ms = sum;
+  if (launches) *launches = (long long)(g_prof_used / 2);
+  g_prof_used = 0;
+  return DIST_OK;
+}
 
 int dist_device_supports_tc(int device) {
   int major = 0;

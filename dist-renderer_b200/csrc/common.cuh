@@ -57,10 +57,7 @@ struct MlpArgs {
 int mlp_simt_launch(const NetDev& net, int mode, const MlpArgs& a, cudaStream_t stream);
 int mlp_tc_launch(const dist_net_t* net, const NetDev& nd, int mode, const MlpArgs& a, cudaStream_t stream);
 
-inline int mlp_launch(const dist_net_t* net, const NetDev& nd, int engine, int mode, const MlpArgs& a,
-                      cudaStream_t stream) {
-  if (engine == DIST_ENGINE_TC) return mlp_tc_launch(net, nd, mode, a, stream);
-  return mlp_simt_launch(nd, mode, a, stream);
-}
+// engine dispatch; brackets the launch with CUDA events while dist_profile_begin() is active (abi.cu)
+int mlp_launch(const dist_net_t* net, const NetDev& nd, int engine, int mode, const MlpArgs& a, cudaStream_t stream);
 
 }  // namespace dist

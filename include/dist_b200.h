@@ -140,6 +140,12 @@ int dist_abi_version(void);
 const char* dist_last_error(void);
 /* number of CUDA kernels this library has launched in this process so far */
 long long dist_launch_count(void);
+/* Kernel timing for roofline accounting (off by default, no cost when off).  While enabled, every decoder-row kernel
+ * launch (the dominant kernel: dist_decoder_* and the launches inside dist_render_*) is bracketed by a pair of CUDA
+ * events on its own stream.  dist_profile_end synchronises those events, returns the number of bracketed launches and
+ * their summed duration in milliseconds, and switches timing off.  Not thread-safe; at most 65536 launches per window. */
+int dist_profile_begin(void);
+int dist_profile_end(double* total_ms, long long* launches);
 /* 1 if the device has the tcgen05 path (compute capability 10.x) */
 int dist_device_supports_tc(int device);
 

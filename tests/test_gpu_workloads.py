@@ -148,6 +148,28 @@ def test_render_views_equals_separate_renders():
         ren.render_views(l_b, Rs[:0], Ts[:0])
 
 
+def test_profile_window_counts_decoder_launches():
+    """dist_profile_begin/end: every decoder-row launch inside the window is event-timed, none outside it."""
+    import ctypes
+    import importlib
+    abi = importlib.import_module("dist-renderer_b200._abi")
+    lib = abi.lib()
+    dec, lat = gu.gpu_decoder("B"), synth.make_latent().cuda()
+    pts = (torch.rand(5000, 3) - 0.5).cuda()
+    pkg.decode_sdf(dec, lat, pts, no_grad=True)                      # engine preparation happens outside the window
+    abi.check(lib.dist_profile_begin())
+    for _ in range(3):
+        pkg.decode_sdf(dec, lat, pts, no_grad=True)
+    pkg.decode_sdf_gradient(dec, lat, pts.clone().requires_grad_(True))
+    ms, n = ctypes.c_double(-1.0), ctypes.c_longlong(-1)
+    abi.check(lib.dist_profile_end(ctypes.byref(ms), ctypes.byref(n)))
+    assert n.value == 4 and 0.0 < ms.value < 50.0
+    pkg.decode_sdf(dec, lat, pts, no_grad=True)
+    abi.check(lib.dist_profile_begin())
+    abi.check(lib.dist_profile_end(ctypes.byref(ms), ctypes.byref(n)))
+    assert n.value == 0 and ms.value == 0.0
+
+
 def test_render_warp_matches_oracle():
     """next-1: SDFRenderer_warp.render_warp (two-view reprojection + photometric L1) vs the pinned CPU restatement."""
     import importlib
