@@ -35,7 +35,7 @@ class Camera(C.Structure):
     _fields_ = [("Kinv", C.c_float * 9), ("M", C.c_float * 9), ("Mn", C.c_float * 9), ("R", C.c_void_p),
                 ("cam_pos", C.c_void_p),
                 ("width", C.c_int32), ("height", C.c_int32), ("row0", C.c_int32), ("row_step", C.c_int32),
-                ("n_rows", C.c_int32), ("radius", C.c_float)]
+                ("n_rows", C.c_int32), ("radius", C.c_float), ("n_views", C.c_int32)]
 
 
 class March(C.Structure):
@@ -45,7 +45,8 @@ class March(C.Structure):
 
 
 WS_FIELDS = ["ray", "entry", "exit_", "dist", "z", "flags", "nreal", "top_sdf", "top_pt", "top_zafter", "top_zgen",
-             "list_a", "list_b", "pts", "sdf", "counts", "sdf_origin", "entry0", "top_lvl", "pyr_f", "pyr_i", "pyr_b"]
+             "list_a", "list_b", "pts", "sdf", "counts", "sdf_origin", "entry0", "top_lvl", "pyr_f", "pyr_i", "pyr_b",
+             "view_stat"]
 
 
 class Workspace(C.Structure):

@@ -17,11 +17,36 @@ namespace {
 
 struct Cam {
   float Kinv[9], M[9], Mn[9];
-  const float* R;
-  const float* c;
+  const float* R;      // [n_views][9]
+  const float* c;      // [n_views][3]
   int W, H, row0, row_step, n_rows;
+  int n_views, Pv;     // views rendered by this call, pixels per view (W * n_rows); global pixel lp = v * Pv + lpv
   float radius;
 };
+
+// per-view bookkeeping of a multi-view call (ws.view_stat, [n_views][4] int32): live rays at step 0, executed march
+// steps (renderer.py:562 breaks per render, i.e. per view), float bits of the coarsest level's largest sphere entry
+enum { VS_LIVE0 = 0, VS_STEPS = 1, VS_MAXENTRY = 2, VS_STRIDE = 4 };
+
+__device__ __forceinline__ void load_view(const Cam& cam, int v, float (&R)[9], float (&c)[3]) {
+#pragma unroll
+  for (int i = 0; i < 9; ++i) R[i] = cam.R[9 * v + i];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) c[i] = cam.c[3 * v + i];
+}
+__device__ __forceinline__ void load_view_pos(const Cam& cam, int v, float (&c)[3]) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i) c[i] = cam.c[3 * v + i];
+}
+// one atomic per (warp, view) instead of one per thread; every lane of the warp must call it (v < 0: nothing to add)
+__device__ __forceinline__ void view_atomic_add(int32_t* view_stat, int slot, int v) {
+  const unsigned peers = __match_any_sync(0xffffffffu, v);
+  if (v >= 0 && (int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(view_stat + VS_STRIDE * v + slot, __popc(peers));
+}
+__device__ __forceinline__ void view_atomic_max(int32_t* view_stat, int slot, int v, int value) {
+  const unsigned peers = __match_any_sync(0xffffffffu, v);
+  if (v >= 0 && (int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicMax(view_stat + VS_STRIDE * v + slot, value);
+}
 
 __device__ __forceinline__ int warp_append(int32_t* counter, bool pred) {
   const unsigned m = __ballot_sync(0xffffffffu, pred);
@@ -45,8 +70,9 @@ __device__ __forceinline__ void coord_ray(const Cam& cam, const float* R, float 
 #pragma unroll
   for (int i = 0; i < 3; ++i) ray[i] = v[i] / nrm;
 }
-__device__ __forceinline__ void pixel_ray(const Cam& cam, const float* R, int lp, float (&ray)[3]) {
-  coord_ray(cam, R, (float)(lp % cam.W), (float)(cam.row0 + (lp / cam.W) * cam.row_step), ray);
+// lpv: pixel index inside its view
+__device__ __forceinline__ void pixel_ray(const Cam& cam, const float* R, int lpv, float (&ray)[3]) {
+  coord_ray(cam, R, (float)(lpv % cam.W), (float)(cam.row0 + (lpv / cam.W) * cam.row_step), ray);
 }
 
 // unit-sphere geometry of one ray (renderer.py:225-282): distance to the origin, hit flag, entry and exit depth
@@ -91,7 +117,7 @@ __device__ __forceinline__ void topk_insert(const dist_workspace_t& ws, int P, i
 
 // One coarse level of the pyramid (renderer.py:713-805): arrays carved from ws.pyr_{f,i,b}
 struct Level {
-  int w, h, P, scale;       // scale = 4 (1/4 resolution) or 2
+  int w, h, Pv, P, scale;   // per-view w x h = Pv pixels, P = n_views * Pv; scale = 4 (1/4 resolution) or 2
   float *ray, *start, *z, *s_sdf, *s_pt, *s_zabs, *s_zgen;   // [3][P], [P], [P], [3][P], [3][3][P], [3][P], [3][P]
   uint8_t* hit;             // [P] max-pooled sphere-hit mask (renderer.py:668-680)
   int32_t* list;            // [P]
@@ -116,15 +142,13 @@ __global__ void k_setup(Cam cam, dist_march_t mp, dist_workspace_t ws, float* Zd
   const int lp = blockIdx.x * blockDim.x + threadIdx.x;
   const bool in = lp < P;
   const bool pyr = mp.marching_type == DIST_MARCH_PYRAMID;
-  float R[9], c[3];
-#pragma unroll
-  for (int i = 0; i < 9; ++i) R[i] = cam.R[i];
-#pragma unroll
-  for (int i = 0; i < 3; ++i) c[i] = cam.c[i];
+  float R[9], c[3] = {0.f, 0.f, 0.f};
+  const int v = in ? lp / cam.Pv : 0, lpv = lp - v * cam.Pv;
   bool live = false;
   float ray[3] = {0.f, 0.f, 1.f}, start = 0.f;
   if (in) {
-    pixel_ray(cam, R, lp, ray);
+    load_view(cam, v, R, c);
+    pixel_ray(cam, R, lpv, ray);
     float dist, entry, ex;
     bool hit;
     sphere_geom(c, ray, cam.radius, dist, hit, entry, ex);
@@ -144,8 +168,8 @@ __global__ void k_setup(Cam cam, dist_march_t mp, dist_workspace_t ws, float* Zd
     if (pyr) {
       // the full-resolution march starts at the parent's last depth (renderer.py:769) and inherits the samples taken
       // on the grandparent and parent rays (index up-sampling, renderer.py:787-801)
-      const int x = lp % cam.W, y = lp / cam.W;
-      const int p1 = (y >> 1) * L1.w + (x >> 1), p2 = (y >> 2) * L2.w + (x >> 2);
+      const int x = lpv % cam.W, y = lpv / cam.W;
+      const int p1 = v * L1.Pv + (y >> 1) * L1.w + (x >> 1), p2 = v * L2.Pv + (y >> 2) * L2.w + (x >> 2);
       start = L1.start[p1] + (L1.hit[p1] ? L1.z[p1] : 0.f);
       if (hit) {
         for (int lv = 2; lv >= 1; --lv) {
@@ -167,6 +191,7 @@ __global__ void k_setup(Cam cam, dist_march_t mp, dist_workspace_t ws, float* Zd
     }
     live = hit && (mp.marching_type == DIST_MARCH_TRIVIAL || (0.f + start < ex));  // renderer.py:526
   }
+  view_atomic_add(ws.view_stat, VS_LIVE0, live ? v : -1);
   const int idx = warp_append(ws.counts + 0, live);
   if (idx >= 0) {
     float p[3];
@@ -182,26 +207,22 @@ __global__ void k_hit_flags(Cam cam, dist_workspace_t ws, int P) {
   if (lp >= P) return;
   float R[9], c[3], ray[3], dist, entry, ex;
   bool hit;
-#pragma unroll
-  for (int i = 0; i < 9; ++i) R[i] = cam.R[i];
-#pragma unroll
-  for (int i = 0; i < 3; ++i) c[i] = cam.c[i];
-  pixel_ray(cam, R, lp, ray);
+  const int v = lp / cam.Pv;
+  load_view(cam, v, R, c);
+  pixel_ray(cam, R, lp - v * cam.Pv, ray);
   sphere_geom(c, ray, cam.radius, dist, hit, entry, ex);
   ws.flags[lp] = hit ? 1 : 0;
 }
 
 // coarse level: rays through the pooled pixel centres, own sphere entry, max-pooled hit mask (renderer.py:604-680)
-__global__ void k_pyr_rays(Cam cam, Level L, const uint8_t* fine_hit, int fine_w, int fine_h, int fine_is_flags, float* maxentry) {
+__global__ void k_pyr_rays(Cam cam, Level L, const uint8_t* fine_hit, int fine_w, int fine_h, int32_t* view_stat) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= L.P) return;
-  const int ix = i % L.w, iy = i / L.w;
+  const int v = i / L.Pv, il = i - v * L.Pv;
+  const int ix = il % L.w, iy = il / L.w;
   float R[9], c[3], ray[3], dist, entry, ex;
   bool ownhit;
-#pragma unroll
-  for (int k = 0; k < 9; ++k) R[k] = cam.R[k];
-#pragma unroll
-  for (int k = 0; k < 3; ++k) c[k] = cam.c[k];
+  load_view(cam, v, R, c);
   const float off = ((float)L.scale - 1.f) / 2.f;
   coord_ray(cam, R, (float)L.scale * (float)ix + off, (float)L.scale * (float)iy + off, ray);
   sphere_geom(c, ray, cam.radius, dist, ownhit, entry, ex);
@@ -210,28 +231,29 @@ __global__ void k_pyr_rays(Cam cam, Level L, const uint8_t* fine_hit, int fine_w
   for (int dy = 0; dy < 2; ++dy)
     for (int dx = 0; dx < 2; ++dx) {
       const int fx = 2 * ix + dx, fy = 2 * iy + dy;
-      if (fx < fine_w && fy < fine_h) pooled |= (fine_hit[fy * fine_w + fx] & 1) != 0;
+      if (fx < fine_w && fy < fine_h) pooled |= (fine_hit[(size_t)v * fine_w * fine_h + fy * fine_w + fx] & 1) != 0;
     }
-  (void)fine_is_flags;
   L.hit[i] = pooled ? 1 : 0;
   L.z[i] = 0.f;
   // coarsest level: own entry where the coarse ray meets the sphere, else the largest entry of those that do
   // (renderer.py:270-272); stash the own entry, resolve after the max is known
   L.start[i] = ownhit ? entry : -1.f;
-  if (maxentry && ownhit) atomicMax(reinterpret_cast<int*>(maxentry), __float_as_int(fmaxf(entry, 0.f)));
+  if (view_stat && ownhit) atomicMax(view_stat + VS_STRIDE * v + VS_MAXENTRY, __float_as_int(fmaxf(entry, 0.f)));
 }
 
 // start depth of a coarse level + its (fixed) active list and first query points
-__global__ void k_pyr_start(Cam cam, Level L, Level parent, int has_parent, const float* maxentry, float* pts) {
+__global__ void k_pyr_start(Cam cam, Level L, Level parent, int has_parent, const int32_t* view_stat, float* pts) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   bool on = false;
   float start = 0.f;
+  const int v = (i < L.P) ? i / L.Pv : 0;
   if (i < L.P) {
     if (has_parent) {
-      const int ix = i % L.w, iy = i / L.w, pp = (iy >> 1) * parent.w + (ix >> 1);
+      const int il = i - v * L.Pv;
+      const int ix = il % L.w, iy = il / L.w, pp = v * parent.Pv + (iy >> 1) * parent.w + (ix >> 1);
       start = parent.start[pp] + (parent.hit[pp] ? parent.z[pp] : 0.f);   // renderer.py:769,779
     } else {
-      start = (L.start[i] >= 0.f) ? L.start[i] : *maxentry;
+      start = (L.start[i] >= 0.f) ? L.start[i] : __int_as_float(view_stat[VS_STRIDE * v + VS_MAXENTRY]);
     }
     L.start[i] = start;
     on = L.hit[i] != 0;
@@ -239,8 +261,7 @@ __global__ void k_pyr_start(Cam cam, Level L, Level parent, int has_parent, cons
   const int idx = warp_append(L.count, on);
   if (idx >= 0) {
     float c[3], ray[3] = {L.ray[i], L.ray[L.P + i], L.ray[2 * L.P + i]}, p[3];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) c[k] = cam.c[k];
+    load_view_pos(cam, v, c);
     point_on_ray(cam, c, ray, start + 0.f, p);
     L.list[idx] = i;
     pts[(size_t)idx * 3] = p[0]; pts[(size_t)idx * 3 + 1] = p[1]; pts[(size_t)idx * 3 + 2] = p[2];
@@ -251,11 +272,10 @@ __global__ void k_pyr_start(Cam cam, Level L, Level parent, int has_parent, cons
 // recorded per (step, ray); the query point of the next step overwrites this thread's own slot
 __global__ void k_pyr_step(Cam cam, dist_march_t mp, Level L, int step, float* pts, const float* sdfbuf) {
   const int n = *L.count;
-  float c[3];
-#pragma unroll
-  for (int k = 0; k < 3; ++k) c[k] = cam.c[k];
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const int id = L.list[i];
+    float c[3];
+    load_view_pos(cam, id / L.Pv, c);
     const float sdf = sdfbuf[i];
     const float zc = L.z[id], start = L.start[id];
     const float znew = zc + clampf(sdf, mp.clamp_dist) * mp.ratio;
@@ -286,17 +306,15 @@ __global__ void k_march_update(Cam cam, dist_march_t mp, dist_workspace_t ws, in
   const float* pts_cur = ws.pts + (size_t)(step & 1) * (size_t)(P + 1) * 3;       // points of this step
   float* pts_nxt = ws.pts + (size_t)((step + 1) & 1) * (size_t)(P + 1) * 3;       // points of the next step
   if (step == 0 && blockIdx.x == 0 && threadIdx.x == 0) ws.sdf_origin[0] = ws.sdf[n];
-  float c[3];
-#pragma unroll
-  for (int i = 0; i < 3; ++i) c[i] = cam.c[i];
   const int B = mp.buffer_size;
   for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
     const int i = base + threadIdx.x;
     bool live = false;
-    int lp = 0;
+    int lp = 0, v = -1;
     float znew = 0.f, entry = 0.f;
     if (i < n) {
       lp = cur[i];
+      v = lp / cam.Pv;
       const float sdf = ws.sdf[i];
       const float px = pts_cur[(size_t)i * 3], py = pts_cur[(size_t)i * 3 + 1], pz = pts_cur[(size_t)i * 3 + 2];
       const float zc = ws.z[lp];
@@ -314,9 +332,11 @@ __global__ void k_march_update(Cam cam, dist_march_t mp, dist_workspace_t ws, in
         else live = (znew + entry < ws.exit_[lp]) && (asdf >= mp.threshold);  // renderer.py:559-561
       }
     }
+    view_atomic_max(ws.view_stat, VS_STEPS, v, step + 1);   // view v executed this step
     const int idx = warp_append(ws.counts + step + 1, live);
     if (idx >= 0) {
-      float ray[3] = {ws.ray[lp], ws.ray[P + lp], ws.ray[2 * P + lp]}, p[3];
+      float ray[3] = {ws.ray[lp], ws.ray[P + lp], ws.ray[2 * P + lp]}, p[3], c[3];
+      load_view_pos(cam, v, c);
       point_on_ray(cam, c, ray, entry + znew, p);
       nxt[idx] = lp;
       pts_nxt[(size_t)idx * 3] = p[0]; pts_nxt[(size_t)idx * 3 + 1] = p[1]; pts_nxt[(size_t)idx * 3 + 2] = p[2];
@@ -325,18 +345,12 @@ __global__ void k_march_update(Cam cam, dist_march_t mp, dist_workspace_t ws, in
 }
 
 // ---------------------------------------------------------------------------------------------- finalize
-__global__ void k_finalize(dist_march_t mp, dist_workspace_t ws, float* Zdepth, uint8_t* mask, float* min_sdf, int P) {
-  __shared__ int s_steps;
-  if (threadIdx.x == 0) {
-    int s = 0;
-    while (s < mp.march_step && ws.counts[s] > 0) ++s;  // executed steps (early break, renderer.py:562)
-    s_steps = s;
-  }
-  __syncthreads();
+__global__ void k_finalize(dist_march_t mp, dist_workspace_t ws, float* Zdepth, uint8_t* mask, float* min_sdf, int P, int Pv) {
   const int lp = blockIdx.x * blockDim.x + threadIdx.x;
   if (lp >= P || !(ws.flags[lp] & 1)) return;
   const int B = mp.buffer_size;
-  const int S = s_steps;
+  // steps this ray's view executed before all of its rays had finished (the early break of renderer.py:562 is per render)
+  const int S = ws.view_stat[VS_STRIDE * (lp / Pv) + VS_STEPS];
   int nreal = ws.nreal[lp];
   const float so = ws.sdf_origin[0];
   const float zfin = ws.z[lp];
@@ -393,11 +407,9 @@ __global__ void k_normal_gen(Cam cam, const float* Zdepth, const uint8_t* mask, 
   const int idx = warp_append(count, on);
   if (idx >= 0) {
     float R[9], c[3], ray[3], p[3];
-#pragma unroll
-    for (int i = 0; i < 9; ++i) R[i] = cam.R[i];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) c[i] = cam.c[i];
-    pixel_ray(cam, R, lp, ray);
+    const int v = lp / cam.Pv;
+    load_view(cam, v, R, c);
+    pixel_ray(cam, R, lp - v * cam.Pv, ray);
     point_on_ray(cam, c, ray, Zdepth[lp], p);
     idx_out[idx] = lp;
     pts[(size_t)idx * 3] = p[0]; pts[(size_t)idx * 3 + 1] = p[1]; pts[(size_t)idx * 3 + 2] = p[2];
@@ -449,44 +461,64 @@ __global__ void k_bwd_gen(dist_march_t mp, dist_workspace_t ws, const float* gZ,
 }
 
 __global__ void k_bwd_scatter(Cam cam, dist_workspace_t ws, const int32_t* row_pix, const float* dpts,
-                              const int32_t* count, float* d_cam, float* d_ray, float* d_ray_coarse, int w1, int P1, int w2,
-                              int P2, int P) {
+                              const int32_t* count, float* d_cam, float* d_ray, float* d_ray_coarse, int w1, int P1v, int w2,
+                              int P2v, int P) {
   const int n = *count;
+  const size_t P1 = (size_t)cam.n_views * P1v, P2 = (size_t)cam.n_views * P2v;
+  // d_cam[v] accumulates per thread while consecutive rows stay in one view (rows are generated in pixel order)
   float acc[3] = {0.f, 0.f, 0.f};
+  int acc_v = -1;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const int lp = row_pix[i] / DIST_MAX_BUFFER, b = row_pix[i] % DIST_MAX_BUFFER;
     const float zg = ws.top_zgen[(size_t)b * P + lp];
     if (zg != zg) continue;  // filler / off-ray sample: no camera dependence
+    const int v = lp / cam.Pv, lpv = lp - v * cam.Pv;
+    if (v != acc_v) {
+      if (acc_v >= 0)
+        for (int k = 0; k < 3; ++k)
+          if (acc[k] != 0.f) atomicAdd(d_cam + 3 * acc_v + k, acc[k]);
+      acc[0] = acc[1] = acc[2] = 0.f;
+      acc_v = v;
+    }
     const float d[3] = {dpts[(size_t)i * 3], dpts[(size_t)i * 3 + 1], dpts[(size_t)i * 3 + 2]};
 #pragma unroll
     for (int k = 0; k < 3; ++k) {  // p = M^T q  ->  dL/dq = M dL/dp
-      const float v = fmaf(cam.M[k * 3 + 2], d[2], fmaf(cam.M[k * 3 + 1], d[1], cam.M[k * 3] * d[0]));
-      acc[k] += v;
+      const float g = fmaf(cam.M[k * 3 + 2], d[2], fmaf(cam.M[k * 3 + 1], d[1], cam.M[k * 3] * d[0]));
+      acc[k] += g;
       const int lvl = ws.top_lvl[(size_t)b * P + lp];
-      if (lvl == 0) atomicAdd(d_ray + (size_t)k * P + lp, v * zg);
+      if (lvl == 0) atomicAdd(d_ray + (size_t)k * P + lp, g * zg);
       else if (d_ray_coarse) {   // sample taken on the parent (1/2) or grandparent (1/4 resolution) ray
-        const int x = lp % cam.W, y = lp / cam.W;
-        if (lvl == 1) atomicAdd(d_ray_coarse + (size_t)k * P1 + (y >> 1) * w1 + (x >> 1), v * zg);
-        else atomicAdd(d_ray_coarse + (size_t)3 * P1 + (size_t)k * P2 + (y >> 2) * w2 + (x >> 2), v * zg);
+        const int x = lpv % cam.W, y = lpv / cam.W;
+        if (lvl == 1) atomicAdd(d_ray_coarse + (size_t)k * P1 + (size_t)v * P1v + (y >> 1) * w1 + (x >> 1), g * zg);
+        else atomicAdd(d_ray_coarse + 3 * P1 + (size_t)k * P2 + (size_t)v * P2v + (y >> 2) * w2 + (x >> 2), g * zg);
       }
     }
   }
+  // flush: one atomic per warp when the whole warp ended in the same view, else one per thread
+  const unsigned same = __match_any_sync(0xffffffffu, acc_v);
+  const bool uniform = (same == 0xffffffffu);
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
-    float v = acc[k];
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if ((threadIdx.x & 31) == 0 && v != 0.f) atomicAdd(d_cam + k, v);
+    float t = acc[k];
+    if (uniform) {
+      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+      if ((threadIdx.x & 31) == 0 && acc_v >= 0 && t != 0.f) atomicAdd(d_cam + 3 * acc_v + k, t);
+    } else if (acc_v >= 0 && t != 0.f) {
+      atomicAdd(d_cam + 3 * acc_v + k, t);
+    }
   }
 }
 
 int make_cam(const dist_camera_t* cam, Cam* out) {
   DIST_REQUIRE(cam && cam->R && cam->cam_pos, "camera: null pointer");
   DIST_REQUIRE(cam->width > 0 && cam->n_rows > 0 && cam->row_step > 0, "camera: bad image/tile description");
-  DIST_REQUIRE((int64_t)cam->width * cam->n_rows < (int64_t)(1u << 31) / DIST_MAX_BUFFER, "camera: tile too large");
+  const int n_views = cam->n_views > 0 ? cam->n_views : 1;
+  DIST_REQUIRE((int64_t)cam->width * cam->n_rows * n_views < (int64_t)(1u << 31) / DIST_MAX_BUFFER, "camera: tile too large");
   for (int i = 0; i < 9; ++i) { out->Kinv[i] = cam->Kinv[i]; out->M[i] = cam->M[i]; out->Mn[i] = cam->Mn[i]; }
   out->R = cam->R; out->c = cam->cam_pos;
   out->W = cam->width; out->H = cam->height; out->row0 = cam->row0; out->row_step = cam->row_step;
   out->n_rows = cam->n_rows; out->radius = cam->radius;
+  out->n_views = n_views; out->Pv = cam->width * cam->n_rows;
   return DIST_OK;
 }
 
@@ -501,10 +533,10 @@ static void carve_levels(const Cam& cam, const dist_workspace_t* ws, Level* L1, 
   uint8_t* bb = ws->pyr_b;
   const int w1 = (w + 1) / 2, h1 = (h + 1) / 2, w2 = (w1 + 1) / 2, h2 = (h1 + 1) / 2;
   const int dims[2][2] = {{w1, h1}, {w2, h2}};
-  int32_t* counts = li + (size_t)w1 * h1 + (size_t)w2 * h2;
+  int32_t* counts = li + ((size_t)w1 * h1 + (size_t)w2 * h2) * cam.n_views;
   for (int i = 0; i < 2; ++i) {
     Level& L = *Ls[i];
-    L.w = dims[i][0]; L.h = dims[i][1]; L.P = L.w * L.h; L.scale = (i == 0) ? 2 : 4;
+    L.w = dims[i][0]; L.h = dims[i][1]; L.Pv = L.w * L.h; L.P = L.Pv * cam.n_views; L.scale = (i == 0) ? 2 : 4;
     L.ray = f; f += 3 * (size_t)L.P;
     L.start = f; f += L.P;
     L.z = f; f += L.P;
@@ -532,9 +564,10 @@ int render_depth_fwd(const dist_net_t* net, int engine, const dist_camera_t* cam
   DIST_REQUIRE(mp->buffer_size >= 1 && mp->buffer_size <= DIST_MAX_BUFFER, "buffer_size must be in [1,%d]", DIST_MAX_BUFFER);
   DIST_REQUIRE(mp->march_step >= 1, "march_step must be >= 1");
   DIST_REQUIRE(mp->marching_type >= DIST_MARCH_TRIVIAL && mp->marching_type <= DIST_MARCH_PYRAMID, "bad marching_type");
-  DIST_REQUIRE(ws->entry0 && ws->top_lvl, "workspace: entry0 / top_lvl missing");
+  DIST_REQUIRE(ws->entry0 && ws->top_lvl && ws->view_stat, "workspace: entry0 / top_lvl / view_stat missing");
   const bool pyr = mp->marching_type == DIST_MARCH_PYRAMID;
-  const int P = cam.W * cam.n_rows;
+  const int P = cam.Pv * cam.n_views;
+  DIST_CHECK_CUDA(cudaMemsetAsync(ws->view_stat, 0, sizeof(int32_t) * VS_STRIDE * cam.n_views, st));
   const int S_total = mp->march_step;
   const int tb = 256, gb = (P + tb - 1) / tb;
   Level L1, L2;
@@ -547,14 +580,13 @@ int render_depth_fwd(const dist_net_t* net, int engine, const dist_camera_t* cam
     carve_levels(cam, ws, &L1, &L2);
     mp->march_step = S_total - mp->coarse_steps[0] - mp->coarse_steps[1];   // renderer.py:724-725
     mp->first_query_check = 0;                                               // renderer.py:795
-    float* maxentry = reinterpret_cast<float*>(L1.count + 2);
     DIST_CHECK_CUDA(cudaMemsetAsync(L1.count, 0, sizeof(int32_t) * 8, st));
     k_hit_flags<<<gb, tb, 0, st>>>(cam, *ws, P); count_launch();
-    k_pyr_rays<<<(L1.P + tb - 1) / tb, tb, 0, st>>>(cam, L1, ws->flags, cam.W, cam.n_rows, 1, nullptr); count_launch();
-    k_pyr_rays<<<(L2.P + tb - 1) / tb, tb, 0, st>>>(cam, L2, L1.hit, L1.w, L1.h, 0, maxentry); count_launch();
+    k_pyr_rays<<<(L1.P + tb - 1) / tb, tb, 0, st>>>(cam, L1, ws->flags, cam.W, cam.n_rows, nullptr); count_launch();
+    k_pyr_rays<<<(L2.P + tb - 1) / tb, tb, 0, st>>>(cam, L2, L1.hit, L1.w, L1.h, ws->view_stat); count_launch();
     for (int lv = 2; lv >= 1; --lv) {
       Level& L = (lv == 2) ? L2 : L1;
-      k_pyr_start<<<(L.P + tb - 1) / tb, tb, 0, st>>>(cam, L, L2, lv == 1 ? 1 : 0, maxentry, ws->pts); count_launch();
+      k_pyr_start<<<(L.P + tb - 1) / tb, tb, 0, st>>>(cam, L, L2, lv == 1 ? 1 : 0, ws->view_stat, ws->pts); count_launch();
       const int ns = mp->coarse_steps[2 - lv];
       for (int s = 0; s < ns; ++s) {
         MlpArgs a{};
@@ -580,7 +612,7 @@ int render_depth_fwd(const dist_net_t* net, int engine, const dist_camera_t* cam
     if (rc) return rc;
     k_march_update<<<gu, tb, 0, st>>>(cam, *mp, *ws, s, P); count_launch();
   }
-  k_finalize<<<gb, tb, 0, st>>>(*mp, *ws, Zdepth, mask, min_sdf, P); count_launch();
+  k_finalize<<<gb, tb, 0, st>>>(*mp, *ws, Zdepth, mask, min_sdf, P, cam.Pv); count_launch();
   DIST_CHECK_CUDA(cudaGetLastError());
   return DIST_OK;
 }
@@ -594,7 +626,7 @@ int render_normal_fwd(const dist_net_t* net, int engine, const dist_camera_t* ca
   NetDev nd;
   rc = make_netdev(net, &nd);
   if (rc) return rc;
-  const int P = cam.W * cam.n_rows;
+  const int P = cam.Pv * cam.n_views;
   DIST_CHECK_CUDA(cudaMemsetAsync(s_count, 0, sizeof(int32_t), st));
   DIST_CHECK_CUDA(cudaMemsetAsync(Znormal, 0, sizeof(float) * 3 * (size_t)P, st));
   const int tb = 256, gb = (P + tb - 1) / tb;
@@ -620,7 +652,7 @@ int render_depth_bwd(const dist_net_t* net, int engine, const dist_camera_t* cam
   NetDev nd;
   rc = make_netdev(net, &nd);
   if (rc) return rc;
-  const int P = cam.W * cam.n_rows;
+  const int P = cam.Pv * cam.n_views;
   DIST_CHECK_CUDA(cudaMemsetAsync(s_count, 0, sizeof(int32_t), st));
   const int tb = 256, gb = (P + tb - 1) / tb;
   k_bwd_gen<<<gb, tb, 0, st>>>(*mp, *ws, gZ, gM, s_row_pix, s_pts, s_coef, s_count, P); count_launch();

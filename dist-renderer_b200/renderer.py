@@ -43,7 +43,9 @@ class _RenderDepthFn(torch.autograd.Function):
         engine = resolve_engine(plan, opts["engine"])
         net, engine, _keep = plan.net_for(latent, engine, st)
         Rd = R.detach().float().contiguous()
-        cam_pos = torch.matmul(-Rd.t(), T.detach().float()[:, None]).squeeze(1).contiguous()  # renderer.py:186
+        if Rd.shape != ((3, 3) if ren.n_views == 1 and R.dim() == 2 else (ren.n_views, 3, 3)):
+            raise ValueError("R must be (3,3), or (n_views,3,3) on a multi-view renderer")
+        cam_pos = ren.get_camera_location(Rd, T.detach().float()).contiguous()  # renderer.py:186
         cam = ren._c_camera(Rd, cam_pos, opts["use_transform"])
         mp = _abi.March(ren.march_step, B, _MARCH[opts["kind"]], 1 if opts["kind"] != "pyramid_recursive" else 0,
                         ren.ray_marching_ratio, ren.threshold, float(opts["clamp_dist"]), 1 if opts["replay"] else 0)
@@ -68,7 +70,7 @@ class _RenderDepthFn(torch.autograd.Function):
         min_sdf = torch.empty(P, **f32)
         _abi.check(lib.dist_render_depth_fwd(net, engine, cam, mp, ws, _abi.ptr(Zdepth), _abi.ptr(mask),
                                              _abi.ptr(min_sdf), _abi.ptr(ren.rows_evaluated), st))
-        ren._last_counts = scr["counts"]
+        ren._last_counts = scr["view_stat"]
         ctx.ren, ctx.opts, ctx.engine, ctx.mp = ren, opts, engine, mp
         ctx.saved = saved
         ctx.save_for_backward(latent, Rd, T.detach().float())
@@ -84,8 +86,9 @@ class _RenderDepthFn(torch.autograd.Function):
         ren, opts, lib, st = ctx.ren, ctx.opts, _abi.lib(), _stream()
         plan, dev, P, B = ren.plan, ren.device, ren.P, ren.buffer_size
         net, eng_b, _keep = plan.net_for(latent, ctx.engine, st)
-        cam_pos = torch.matmul(-Rd.t(), Td[:, None]).squeeze(1).contiguous()
+        cam_pos = ren.get_camera_location(Rd, Td).contiguous()
         cam = ren._c_camera(Rd, cam_pos, opts["use_transform"])
+        V, Pv = ren.n_views, ren.Pv
         scr = ren._scratch()
         ws = _abi.Workspace()
         for name in _abi.WS_FIELDS:
@@ -98,9 +101,9 @@ class _RenderDepthFn(torch.autograd.Function):
         f32 = dict(device=dev, dtype=torch.float32)
         acc0 = torch.zeros(plan.bias[0].numel(), **f32)
         accl = torch.zeros(plan.bias[plan.latent_in].numel(), **f32) if plan.latent_in >= 0 else None
-        d_cam = torch.zeros(3, **f32) if want_cam else None
+        d_cam = torch.zeros(V, 3, **f32) if want_cam else None
         d_ray = torch.zeros(3, P, **f32) if want_cam else None
-        n_coarse = sum(g[0].shape[1] for g in ren._coarse_homo()) if (want_cam and pyr) else 0
+        n_coarse = V * sum(g[0].shape[1] for g in ren._coarse_homo()) if (want_cam and pyr) else 0
         d_ray_c = torch.zeros(3 * n_coarse, **f32) if n_coarse else None
         g_lat = g_R = g_T = None
         if gZ is not None or gM is not None:
@@ -114,15 +117,18 @@ class _RenderDepthFn(torch.autograd.Function):
             if want_cam:
                 with torch.enable_grad():
                     Rg, Tg = Rd.clone().requires_grad_(True), Td.clone().requires_grad_(True)
-                    c = torch.matmul(-Rg.t(), Tg[:, None]).squeeze(1)
-                    outs, gouts = [c, ren.get_camera_rays(Rg)], [d_cam, d_ray]
+                    c = ren.get_camera_location(Rg, Tg)
+
+                    def per_view(g, n):   # kernel layout [3][V*n] -> layout of the host tensor, (3,n) or (V,3,n)
+                        return g.reshape(3, n) if Rg.dim() == 2 else g.reshape(3, V, n).permute(1, 0, 2)
+                    outs, gouts = [c, ren.get_camera_rays(Rg)], [d_cam.reshape(c.shape), per_view(d_ray, Pv)]
                     if d_ray_c is not None:   # samples taken on the 1/2- and 1/4-resolution parent rays
                         off = 0
                         for (homo,) in ren._coarse_homo():
                             n_l = homo.shape[1]
                             outs.append(ren.get_camera_rays(Rg, homo=homo))
-                            gouts.append(d_ray_c[off:off + 3 * n_l].reshape(3, n_l))
-                            off += 3 * n_l
+                            gouts.append(per_view(d_ray_c[off:off + 3 * V * n_l], n_l))
+                            off += 3 * V * n_l
                     g_R, g_T = torch.autograd.grad(outs, [Rg, Tg], gouts, allow_unused=True)
         return g_lat, g_R, g_T, None, None
 
@@ -165,7 +171,9 @@ class SDFRenderer(object):
         if not (0 <= row0 and step >= 1 and n_rows >= 1 and row0 + (n_rows - 1) * step < h):
             raise ValueError("rows=(row0,row_step,n_rows) outside the image")
         self.local_hw = (n_rows, w)
-        self.P = n_rows * w
+        self.n_views = 1             # > 1 only on the children made by _fused_child (multi-view march, render_views)
+        self.Pv = n_rows * w         # pixels per view
+        self.P = self.Pv             # pixels per call = n_views * Pv
         self.K = torch.from_numpy(self.intrinsic).float().to(self.device)
         self.K_inv = torch.from_numpy(np.linalg.inv(self.intrinsic)).float().to(self.device)
         if transform_matrix is None:
@@ -203,7 +211,7 @@ class SDFRenderer(object):
             ys = (row0 + step * torch.arange(n_rows, device=self.device)).float()
             xs = torch.arange(w, device=self.device).float()
             Y, X = torch.meshgrid(ys, xs, indexing="ij")
-            homo = torch.stack([X.reshape(-1), Y.reshape(-1), torch.ones(self.P, device=self.device)], 0)
+            homo = torch.stack([X.reshape(-1), Y.reshape(-1), torch.ones(self.Pv, device=self.device)], 0)
             self._homo_calib = torch.matmul(self.K_inv, homo)
         return self._homo_calib
 
@@ -213,13 +221,20 @@ class SDFRenderer(object):
             self._calib_map = self.normalize_vectors(self.homo_calib)[2, :]  # renderer.py:59
         return self._calib_map
 
+    # The camera helpers accept one pose (R (3,3), T (3,)) -> (3,), (3,P) as in the reference, or a stack of poses
+    # (R (V,3,3), T (V,3)) -> (V,3), (V,3,P).  A stack is evaluated pose by pose with the single-pose ops, so that a
+    # fused multi-view render sees bit-identical cameras to V separate renders (batched GEMMs may round differently).
     def normalize_vectors(self, x):  # renderer.py:171-178
         return x.div(torch.norm(x, p=2, dim=0).expand_as(x) + 1e-12)
 
     def get_camera_location(self, R, T):  # renderer.py:180-188
+        if R.dim() == 3:
+            return torch.stack([self.get_camera_location(R[v], T[v]) for v in range(R.shape[0])], 0)
         return torch.matmul(-R.transpose(1, 0), T[:, None]).squeeze(1)
 
     def get_camera_rays(self, R, homo=None):  # renderer.py:190-200
+        if R.dim() == 3:
+            return torch.stack([self.get_camera_rays(R[v], homo) for v in range(R.shape[0])], 0)
         return self.normalize_vectors(torch.matmul(R.transpose(1, 0), self.homo_calib if homo is None else homo))
 
     def transform_points(self, points):  # renderer.py:84-98
@@ -242,6 +257,8 @@ class SDFRenderer(object):
         return points
 
     def get_distance_from_origin(self, cam_pos, cam_rays):  # renderer.py:225-239
+        if cam_rays.dim() == 3:
+            return torch.stack([self.get_distance_from_origin(cam_pos[v], cam_rays[v]) for v in range(cam_rays.shape[0])], 0)
         ptq = (cam_pos[:, None] * cam_rays).sum(0)
         return torch.norm(cam_pos[:, None] - ptq[None, :] * cam_rays, p=2, dim=0)
 
@@ -258,6 +275,7 @@ class SDFRenderer(object):
         cam.width, cam.height = self.img_hw[1], self.img_hw[0]
         cam.row0, cam.row_step, cam.n_rows = self.rows
         cam.radius = self.radius
+        cam.n_views = self.n_views
         return cam
 
     def _coarse_steps(self):
@@ -292,7 +310,7 @@ class SDFRenderer(object):
         """Reusable (not saved-for-backward) per-renderer device scratch, stream-ordered."""
         if pyramid and self._scr is not None and self._scr.get("pyr_f") is None:
             (h1, w1), (h2, w2) = self._coarse_dims()
-            npc = h1 * w1 + h2 * w2
+            npc = (h1 * w1 + h2 * w2) * self.n_views
             self._scr["pyr_f"] = torch.empty(23 * npc, device=self.device, dtype=torch.float32)
             self._scr["pyr_i"] = torch.empty(npc + 8, device=self.device, dtype=torch.int32)
             self._scr["pyr_b"] = torch.empty(npc, device=self.device, dtype=torch.uint8)
@@ -306,6 +324,7 @@ class SDFRenderer(object):
                 "z": torch.empty(P, **f32), "list_a": torch.empty(P, **i32), "list_b": torch.empty(P, **i32),
                 "pts": torch.empty(2, P + 1, 3, **f32), "sdf": torch.empty(P + 1, **f32),
                 "counts": torch.empty(self.march_step + 2, **i32),
+                "view_stat": torch.zeros(self.n_views, 4, **i32),
                 "n_idx": torch.empty(P, **i32), "n_pts": torch.empty(P, 3, **f32), "n_grad": torch.empty(P, 3, **f32),
                 "n_cnt": torch.empty(1, **i32),
                 # backward replay rows (at most P * buffer_size)
@@ -319,7 +338,7 @@ class SDFRenderer(object):
 
     def _raise_if_empty(self):
         """renderer.py:214-215.  Reads one int back from the device, i.e. waits for the enqueued march."""
-        if int(self._last_counts[0].item()) == 0:
+        if int(self._last_counts[:, 0].min().item()) == 0:   # view_stat[v][0]: rays of view v alive at step 0
             raise ValueError('No valid depth.')
 
     def reset_row_counter(self):
@@ -355,7 +374,7 @@ class SDFRenderer(object):
         if torch.is_grad_enabled() and (R.requires_grad or T.requires_grad):
             # renderer.py:842,863: the fill of rays missing the unit sphere stays differentiable w.r.t. the camera
             cam_pos = self.get_camera_location(R, T)
-            d = self.get_distance_from_origin(cam_pos, self.get_camera_rays(R))
+            d = self.get_distance_from_origin(cam_pos, self.get_camera_rays(R)).reshape(-1)
             min_sdf = torch.where(hit, min_sdf, d + self.threshold - self.radius)
         if no_grad_depth:
             Zdepth = Zdepth.detach()
@@ -375,7 +394,7 @@ class SDFRenderer(object):
         engine = resolve_engine(plan, self.engine)
         net, engine, _keep = plan.net_for(latent, engine, st)
         Rd = R.detach().float().contiguous()
-        cam_pos = torch.matmul(-Rd.t(), T.detach().float()[:, None]).squeeze(1).contiguous()
+        cam_pos = self.get_camera_location(Rd, T.detach().float()).contiguous()
         cam = self._c_camera(Rd, cam_pos, use_transform)
         scr = self._scratch()
         Zd = Zdepth.detach().float().contiguous()
@@ -401,9 +420,23 @@ class SDFRenderer(object):
             latent, R, T, clamp_dist=clamp_dist, sample_index_type=sample_index_type, profile=profile, no_grad=no_grad,
             no_grad_depth=no_grad_depth, no_grad_mask=no_grad_mask, no_grad_camera=no_grad_camera,
             ray_marching_type=ray_marching_type, use_transform=use_transform, check_empty=False)
-        depth = torch.where(valid_mask, Zdepth * self.calib_map, torch.full_like(Zdepth, 1e11))  # renderer.py:967-969
+        V, stacked = self.n_views, R.dim() == 3
+        calib = self.calib_map.repeat(V) if stacked else self.calib_map
+        depth = torch.where(valid_mask, Zdepth * calib, torch.full_like(Zdepth, 1e11))  # renderer.py:967-969
         normal = self.render_normal(latent, R, T, Zdepth, valid_mask, clamp_dist=clamp_dist, no_grad=no_grad_normal,
                                     normalize=normalize_normal, use_transform=use_transform)
+        if stacked:     # a stack of poses marched together (render_views): maps get a leading view axis
+            if num_forward_sampling != 0:
+                raise NotImplementedError("forward sampling is not available on the multi-view march")
+            # pose by pose with the single-pose GEMM on contiguous operands: a batched GEMM may round differently
+            Rn, n3 = (R if not no_grad_normal else R.detach()), normal.reshape(3, V, -1)
+            normal = torch.stack([torch.matmul(Rn[v], n3[:, v].contiguous()) for v in range(V)], 0)   # renderer.py:978
+            normal = torch.cat([normal[:, :1] * (-1), normal[:, 1:]], 1).reshape(V, 3, h, w).permute(0, 2, 3, 1)
+            out = (depth.reshape(V, h, w), normal, valid_mask.reshape(V, h, w).type(torch.uint8),
+                   min_abs_query.reshape(V, h, w))
+            if check_empty:
+                self._raise_if_empty()
+            return out
         normal = torch.matmul(R if not no_grad_normal else R.detach(), normal)  # renderer.py:978
         normal = torch.cat([normal[:1] * (-1), normal[1:]], 0)                   # renderer.py:979
         normal = normal.reshape(3, h, w).permute(1, 2, 0)
@@ -417,34 +450,53 @@ class SDFRenderer(object):
         return out
 
     # ---- multi-view batching ------------------------------------------------------------------------------------
+    def _fused_child(self, V):
+        """Shallow copy of this renderer that marches V views of the same shape in ONE call (n_views = V): private
+        scratch sized for V * Pv pixels, everything else shared."""
+        import copy
+        cache = self.__dict__.setdefault("_fused", {})
+        child = cache.get(V)
+        if child is None:
+            child = copy.copy(self)
+            child.n_views, child.P = V, V * self.Pv
+            child._scr, child._last_counts, child._slots, child._fused = None, None, None, {}
+            cache[V] = child
+        return child
+
     def _view_slots(self, n):
         """n (stream, renderer) pairs: shallow copies of this renderer with private scratch, one CUDA stream each."""
         import copy
         slots = getattr(self, "_slots", None) or []
         while len(slots) < n:
             child = copy.copy(self)
-            child._scr, child._last_counts, child._slots = None, None, None
+            child._scr, child._last_counts, child._slots, child._fused = None, None, None, {}
             slots.append((torch.cuda.Stream(device=self.device), child))
         self._slots = slots
         return slots[:n]
 
-    def render_views(self, latent, Rs, Ts, n_streams=1, **kw):
+    def render_views(self, latent, Rs, Ts, fused=True, n_streams=1, **kw):
         """``render()`` of V camera poses of one shape, batched: returns the outputs of ``render`` stacked along a
-        new leading view axis -- (depth[V,h,w], normal[V,h,w,3], mask[V,h,w] uint8, min_abs_query[V,h,w][, ...]).
+        new leading view axis -- (depth[V,h,w], normal[V,h,w,3], mask[V,h,w] uint8, min_abs_query[V,h,w]).
 
         The multi-view callers of the reference (`optimize_multi.py:62-80`, `renderer_warp.py:108-109`) render their
-        views one after the other and synchronise with the host several times per march step.  Here all V views are
-        enqueued without a single host synchronisation (the 'No valid depth' test of every view is read back once, at
-        the end).  ``n_streams > 1`` additionally spreads the views round-robin over that many CUDA streams, each
-        with private scratch (autograd replays every node on its forward stream, so backward is spread the same
-        way).  Measured on B200 (24 views of 256x256, fwd+bwd): 271 ms looped -> 261 ms batched; extra streams add
-        nothing yet because the persistent decoder kernel claims every SM with a static tile assignment
-        (DESIGN.md section 7).  Results are those of V separate ``render`` calls, bit for bit; gradients reach
-        ``latent``, ``Rs[v]``, ``Ts[v]`` as usual."""
+        views one after the other and synchronise with the host several times per march step.
+
+        ``fused=True`` (default): ONE march over all V * h * w rays (`dist_camera_t.n_views`): one compaction list, one
+        decoder launch per step, one normal launch, one backward replay.  The long tail of a march -- dozens of
+        launches that keep a few SM pairs busy for one tile latency each while the last grazing rays converge -- is
+        paid once instead of V times.  Every view keeps the per-render semantics of the reference (own early break,
+        own 'No valid depth' test, own pyramid levels), so the maps are those of V separate ``render`` calls bit for
+        bit; gradients reach ``latent``, ``Rs``, ``Ts`` as usual.
+        ``fused=False`` (or ``num_forward_sampling != 0``): the views are enqueued one after the other without host
+        synchronisation, optionally round-robin on ``n_streams`` CUDA streams with private scratch."""
         check_empty = kw.pop("check_empty", True)
         V = len(Rs)
         if V == 0 or len(Ts) != V:
             raise ValueError("render_views needs V >= 1 rotations and as many translations")
+        if fused and kw.get("num_forward_sampling", 0) == 0:
+            R = Rs if torch.is_tensor(Rs) else torch.stack(list(Rs), 0)
+            T = Ts if torch.is_tensor(Ts) else torch.stack(list(Ts), 0)
+            return self._fused_child(V).render(latent, R, T, check_empty=check_empty, **kw)
         main = torch.cuda.current_stream(self.device)
         # lazily built caches are created on this stream before any view stream can touch them
         _ = self.calib_map, self._coarse_homo()
@@ -462,7 +514,7 @@ class SDFRenderer(object):
             st, child = slots[v % n_streams]
             with torch.cuda.stream(st if side else main):
                 o = child.render(latent, Rs[v], Ts[v], check_empty=False, **kw)
-                n_valid[v:v + 1].copy_(child._last_counts[:1])
+                n_valid[v:v + 1].copy_(child._last_counts[:, 0])
             outs.append(o)
         if side:
             for st, _ in slots:

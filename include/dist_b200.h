@@ -80,14 +80,19 @@ typedef struct dist_camera {
   float M[9];                 /* matrix whose transpose maps world points into the decoder frame: transform_matrix
                                  (renderer.py:44-48, :119), or identity when use_transform=False; only 3x3 supported */
   float Mn[9];                /* transform_matrix applied to the normals (renderer.py:902) -- always the real one */
-  const float* R;             /* device, [9] row-major world->camera rotation */
-  const float* cam_pos;       /* device, [3]  = -R^T T  (renderer.py:180-188) */
+  const float* R;             /* device, [n_views][9] row-major world->camera rotations */
+  const float* cam_pos;       /* device, [n_views][3]  = -R^T T  (renderer.py:180-188) */
   int32_t width;              /* full image width */
   int32_t height;             /* full image height */
   int32_t row0;               /* first image row rendered by this call (ray-tile sharding) */
   int32_t row_step;           /* stride between rendered rows (interleaved bands) */
   int32_t n_rows;             /* number of rows rendered; local pixel lp = lrow*width + x */
   float radius;               /* unit-sphere radius (renderer.py:23) */
+  int32_t n_views;            /* views of the same shape marched by ONE call (0 or 1: a single view).  All per-pixel
+                                 arrays then hold n_views * n_rows * width entries, view-major: the multi-view loops of
+                                 optimize_multi.py:62-80 / renderer_warp.py:108-109 become one march, one compaction
+                                 list, one tail.  Each view keeps the per-render semantics of the reference (its own
+                                 early break, 'No valid depth' test, pyramid levels). */
 } dist_camera_t;
 
 /* March parameters (renderer.py:13 ctor arguments + render_depth arguments). */
@@ -104,7 +109,7 @@ typedef struct dist_march {
 } dist_march_t;
 
 /*
- * Per-render device workspace, all arrays sized by the number of local pixels P = n_rows*width
+ * Per-render device workspace, all arrays sized by the number of local pixels P = n_views*n_rows*width
  * (B = buffer_size).  The top-B sample records double as the tensors saved for backward.
  */
 typedef struct dist_workspace {
@@ -130,9 +135,13 @@ typedef struct dist_workspace {
   uint8_t* top_lvl;  /* [B][P] pyramid level the sample was taken at (0 = this ray; 1, 2 = parent / grandparent ray) */
   /* DIST_MARCH_PYRAMID only (renderer.py:713-805).  With (w1,h1) = ceil((w,h)/2), (w2,h2) = ceil((w1,h1)/2),
    * P1 = w1*h1, P2 = w2*h2:  pyr_f: 23*(P1+P2) floats, pyr_i: (P1+P2)+8 int32, pyr_b: (P1+P2) bytes. */
-  float* pyr_f;
+  float* pyr_f;      /* (all three scale with n_views) */
   int32_t* pyr_i;
   uint8_t* pyr_b;
+  int32_t* view_stat; /* [n_views][4] per-view bookkeeping, zeroed by dist_render_depth_fwd: [0] rays alive at step 0
+                         (0 <=> the reference raises 'No valid depth', renderer.py:214), [1] march steps the view
+                         executed before its early break (renderer.py:562), [2] float bits of the largest coarse-level
+                         sphere entry (renderer.py:270-272), [3] reserved */
 } dist_workspace_t;
 
 /* ---- library ---- */

@@ -117,35 +117,48 @@ def test_multi_view_ring_gradients():
 
 
 def test_render_views_equals_separate_renders():
-    """Batched multi-view render (views in flight on several CUDA streams): forward outputs are bit-identical to V
-    separate render() calls, the gradients over the shared latent and the per-view cameras agree (the latent
-    gradient is accumulated with atomics, so to rounding)."""
-    hw = (48, 48)
+    """Multi-view render: ONE fused march over all views (dist_camera_t.n_views), or the views enqueued back to back /
+    on several streams.  Forward maps are bit-identical to V separate render() calls; the gradients over the shared
+    latent and the per-view cameras agree (they are accumulated with atomics, so to rounding)."""
+    hw = (48, 40)
     views = synth.ring_cameras(24, 25.0, 2.5)[::4]
     K = synth.intrinsic(*hw, focal_scale=1.2 * 2.5 / 1.6)
     ren = pkg.SDFRenderer(gu.gpu_decoder("B"), K, img_hw=hw, march_step=50, buffer_size=5)
-    for kind in ("recursive", "pyramid_recursive"):
+    V = len(views)
+    for kind in ("recursive", "pyramid_recursive", "trivial"):
         Rs = torch.stack([R for R, _ in views]).cuda().requires_grad_(True)
         Ts = torch.stack([T for _, T in views]).cuda().requires_grad_(True)
         l_a = synth.make_latent().cuda().requires_grad_(True)
-        outs = [ren.render(l_a, Rs[v], Ts[v], ray_marching_type=kind) for v in range(len(views))]
+        outs = [ren.render(l_a, Rs[v], Ts[v], ray_marching_type=kind) for v in range(V)]
         sum(cases.scalar_loss(o) for o in outs).backward()
         gR, gT = Rs.grad.clone(), Ts.grad.clone()
-        Rs.grad, Ts.grad = None, None
         l_b = synth.make_latent().cuda().requires_grad_(True)
-        for n_streams in (3, 1):
+        for mode in (dict(fused=True), dict(fused=False, n_streams=3), dict(fused=False, n_streams=1)):
             l_b.grad, Rs.grad, Ts.grad = None, None, None
-            batched = ren.render_views(l_b, Rs, Ts, n_streams=n_streams, ray_marching_type=kind)
-            assert batched[0].shape == (len(views),) + hw and batched[1].shape == (len(views),) + hw + (3,)
-            assert batched[2].dtype == torch.uint8
-            for v, o in enumerate(outs):
-                for a, b in zip(o, batched):
-                    assert torch.equal(a.detach(), b[v].detach())
-            sum(cases.scalar_loss(tuple(b[v] for b in batched)) for v in range(len(views))).backward()
+            batched = ren.render_views(l_b, Rs, Ts, ray_marching_type=kind, **mode)
+            assert batched[0].shape == (V,) + hw and batched[1].shape == (V,) + hw + (3,)
+            assert batched[2].dtype == torch.uint8 and batched[3].shape == (V,) + hw
+            bad = [(kind, mode, v, name, float((a.detach().float() - b[v].detach().float()).abs().max()))
+                   for v, o in enumerate(outs) for name, a, b in zip(("depth", "normal", "mask", "min_sdf"), o, batched)
+                   if not torch.equal(a.detach(), b[v].detach())]
+            assert not bad, bad
+            sum(cases.scalar_loss(tuple(b[v] for b in batched)) for v in range(V)).backward()
             assert gu.rel(l_b.grad.cpu(), l_a.grad.cpu()) < 1e-5
             assert gu.rel(Rs.grad.cpu(), gR.cpu()) < 1e-5 and gu.rel(Ts.grad.cpu(), gT.cpu()) < 1e-5
+    with torch.no_grad():      # forward-only, list inputs
+        b2 = ren.render_views(l_b, [R.cuda() for R, _ in views], [T.cuda() for _, T in views], no_grad=True)
+        o2 = ren.render(l_b, views[1][0].cuda(), views[1][1].cuda(), no_grad=True)
+        assert all(torch.equal(a, b[1]) for a, b in zip(o2, b2))
     with pytest.raises(ValueError):
         ren.render_views(l_b, Rs[:0], Ts[:0])
+    # one view whose rays all pass far from the unit sphere: the reference raises for that render ('No valid depth'),
+    # and so does the multi-view call, whichever way it is executed
+    T_away = Ts.detach().clone()
+    R_away = Rs.detach().clone()
+    R_away[2], T_away[2] = torch.eye(3).cuda(), torch.tensor([50.0, 0.0, 1.6]).cuda()
+    for mode in (dict(fused=True), dict(fused=False)):
+        with pytest.raises(ValueError):
+            ren.render_views(l_b.detach(), R_away, T_away, ray_marching_type="recursive", no_grad=True, **mode)
 
 
 def test_profile_window_counts_decoder_launches():

@@ -1,5 +1,6 @@
 """BASELINE.json config 4 (24 views of 256x256 on the ring, one shape, summed loss, one backward over the latent):
-views rendered one after the other vs. `render_views` with the views in flight on several CUDA streams."""
+views rendered one after the other vs. `render_views` (back to back without host syncs / on several streams /
+one fused march over all views)."""
 import importlib, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -29,9 +30,14 @@ for kind in ("recursive", "pyramid_recursive"):
         sum(bench.loss_of(ren.render(l, Rs[v], Ts[v], ray_marching_type=kind)) for v in range(24)).backward()
     ms = timeit(looped)
     print("%-18s looped          : %7.1f ms  %6.3f M rays/s" % (kind, ms, 24 * 65536 / ms / 1e3), flush=True)
-    for ns in (1, 2, 4, 8):
+    for ns in (1, 4):
         def batched():
             l = lat0.detach().requires_grad_(True)
-            bench.loss_of(ren.render_views(l, Rs, Ts, n_streams=ns, ray_marching_type=kind)).backward()
+            bench.loss_of(ren.render_views(l, Rs, Ts, fused=False, n_streams=ns, ray_marching_type=kind)).backward()
         ms = timeit(batched)
-        print("%-18s render_views x%d : %7.1f ms  %6.3f M rays/s" % (kind, ns, ms, 24 * 65536 / ms / 1e3), flush=True)
+        print("%-18s back to back x%d : %7.1f ms  %6.3f M rays/s" % (kind, ns, ms, 24 * 65536 / ms / 1e3), flush=True)
+    def fused():
+        l = lat0.detach().requires_grad_(True)
+        bench.loss_of(ren.render_views(l, Rs, Ts, ray_marching_type=kind)).backward()
+    ms = timeit(fused)
+    print("%-18s fused march     : %7.1f ms  %6.3f M rays/s" % (kind, ms, 24 * 65536 / ms / 1e3), flush=True)
