@@ -7,7 +7,7 @@ launches on the current stream and chains the tiny camera Jacobian (c = -R^T T, 
 
 Differences from the reference, all loud:
   * no CPU path: ``use_gpu=False`` or a CPU decoder raises;
-  * ``use_depth2normal`` and ``sample_index_type != 'min_abs'`` raise NotImplementedError;
+  * ``sample_index_type != 'min_abs'`` raises NotImplementedError;
     ``pyramid_recursive`` is implemented for the default ``scale_list=[4,2,1]`` on full images;
   * 3x4 ``transform_matrix`` raises (the reference's own 3x4 inverse path calls an un-imported ``pdb``);
   * when no ray meets the unit sphere the reference dies inside ``.max()`` of an empty tensor; here
@@ -413,8 +413,6 @@ class SDFRenderer(object):
         """(depth[h,w], normal[h,w,3], mask[h,w] uint8, min_abs_query[h,w]) -- renderer.py:943-999."""
         if no_grad:
             no_grad_depth, no_grad_normal, no_grad_mask, no_grad_camera = True, True, True, True
-        if self.use_depth2normal:
-            raise NotImplementedError("use_depth2normal is outside the fused path")
         h, w = self.local_hw
         Zdepth, valid_mask, min_abs_query = self.render_depth(
             latent, R, T, clamp_dist=clamp_dist, sample_index_type=sample_index_type, profile=profile, no_grad=no_grad,
@@ -423,6 +421,24 @@ class SDFRenderer(object):
         V, stacked = self.n_views, R.dim() == 3
         calib = self.calib_map.repeat(V) if stacked else self.calib_map
         depth = torch.where(valid_mask, Zdepth * calib, torch.full_like(Zdepth, 1e11))  # renderer.py:967-969
+        if self.use_depth2normal:
+            # renderer.py:972-975: normals by central differences of the depth map; like the reference's helper this
+            # zeroes the background of the returned depth map in place (render_utils.py:24-25)
+            from .render_utils import depth2normal
+            fx, fy = np.float32(self.intrinsic[0, 0]), np.float32(self.intrinsic[1, 1])
+            dmap = depth.reshape((V, h, w) if stacked else (h, w))
+            normal = torch.stack([depth2normal(dmap[v], fx, fy) for v in range(V)], 0) if stacked \
+                else depth2normal(dmap, fx, fy)
+            out = (dmap, normal, valid_mask.reshape(dmap.shape).type(torch.uint8), min_abs_query.reshape(dmap.shape))
+            if num_forward_sampling != 0:
+                if stacked:
+                    raise NotImplementedError("forward sampling is not available on the multi-view march")
+                inside = self.forward_sampling(latent, R, T, Zdepth, valid_mask, clamp_dist=clamp_dist,
+                                               num_forward_sampling=num_forward_sampling, use_transform=use_transform)
+                out = out + (inside.reshape(h, w, num_forward_sampling),)
+            if check_empty:
+                self._raise_if_empty()
+            return out
         normal = self.render_normal(latent, R, T, Zdepth, valid_mask, clamp_dist=clamp_dist, no_grad=no_grad_normal,
                                     normalize=normalize_normal, use_transform=use_transform)
         if stacked:     # a stack of poses marched together (render_views): maps get a leading view axis

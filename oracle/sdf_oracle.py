@@ -71,13 +71,35 @@ def _put(base, mask, src):
     return base.index_copy(0, idx, src)
 
 
+def depth2normal(depth, f_pix_x, f_pix_y=None):
+    """Normal map (H, W, 3) from central differences of a depth map (H, W) -- core/utils/render_utils.py:9-43.
+    Background (depth > 1e5 or == 0) is zeroed IN PLACE in `depth` (:24-25) and gets a zero normal (:42); the shifted
+    copies leave a one-pixel border of zeros (:27-34)."""
+    f_pix_y = f_pix_x if f_pix_y is None else f_pix_y
+    h, w = depth.shape
+    bg = (depth > 1e5) | (depth == 0)
+    depth[bg] = 0.0
+    left, right, up, down = (torch.zeros(h, w, dtype=depth.dtype) for _ in range(4))
+    left[:, 1:w - 1] = depth[:, :w - 2].clone()
+    right[:, 1:w - 1] = depth[:, 2:].clone()
+    up[1:h - 1, :] = depth[:h - 2, :].clone()
+    down[1:h - 1, :] = depth[2:, :].clone()
+    dzdx = (right - left) * f_pix_x / 2.0                                            # :36
+    dzdy = (down - up) * f_pix_y / 2.0                                               # :37
+    n = torch.stack([dzdx, dzdy, -torch.ones_like(dzdx)]).permute(1, 2, 0)           # :39
+    n = n / (torch.norm(n, p=2, dim=2) + 1e-12)[:, :, None]                          # :40-41
+    n[bg] = 0.0
+    return n
+
+
 class OracleSDFRenderer(object):
     def __init__(self, decoder, intrinsic, img_hw=None, transform_matrix=None, march_step=50, buffer_size=5,
                  ray_marching_ratio=1.5, radius=1.0, threshold=5e-5, scale_list=(4, 2, 1),
-                 march_step_list=(3, 3, -1), dtype=torch.float32):
+                 march_step_list=(3, 3, -1), dtype=torch.float32, use_depth2normal=False):
         # renderer.py:13-59
         self.decoder = decoder
         self.dtype = dtype
+        self.use_depth2normal = use_depth2normal
         self.march_step, self.buffer_size = march_step, buffer_size
         self.ratio, self.radius, self.threshold = ray_marching_ratio, radius, threshold
         self.scale_list, self.march_step_list = list(scale_list), list(march_step_list)
@@ -349,6 +371,10 @@ class OracleSDFRenderer(object):
                                                   ray_marching_type=ray_marching_type, use_transform=use_transform)
         depth = torch.ones_like(Zdepth) * 1e11
         depth[mask] = Zdepth[mask].clone() * self.calib_map[mask]
+        if self.use_depth2normal:      # renderer.py:972-975
+            depth = depth.reshape(h, w)
+            normal = depth2normal(depth, np.float32(self.K[0, 0].item()), np.float32(self.K[1, 1].item()))
+            return depth, normal, mask.reshape(h, w).to(torch.uint8), min_map.reshape(h, w)
         normal = self.render_normal(latent, R, T, Zdepth, mask, clamp_dist=clamp_dist, no_grad=no_grad_normal,
                                     normalize=normalize_normal, use_transform=use_transform)
         normal = torch.matmul(R, normal)

@@ -303,6 +303,31 @@ def test_use_transform_false_and_custom_matrix():
         gu.compare([t.cpu() for t in out], [t.detach() for t in ref])
 
 
+def test_use_depth2normal_matches_oracle():
+    """renderer.py:972-975: normals from central differences of the rendered depth (the function itself is pinned to the
+    reference bit for bit on CPU, tests/test_oracle.py); here the wiring and the end-to-end agreement with the oracle."""
+    from oracle.sdf_oracle import OracleSDFRenderer
+    hw = (40, 40)
+    K, R, T = cases.camera(("front", 1.6), hw)
+    lat = cases.synth.make_latent()
+    ora = OracleSDFRenderer(cases.decoder("B"), K, img_hw=hw, use_depth2normal=True)
+    ren = pkg.SDFRenderer(gu.gpu_decoder("B"), K, img_hw=hw, use_depth2normal=True)
+    ref = ora.render(lat, R, T, ray_marching_type="recursive", no_grad=True)
+    out = [t.cpu() for t in ren.render(lat.cuda(), R.cuda(), T.cuda(), ray_marching_type="recursive", no_grad=True)]
+    assert out[0].shape == hw and out[1].shape == hw + (3,) and out[2].dtype == torch.uint8
+    mg, mo = out[2].bool(), ref[2].bool()
+    assert int((mg != mo).sum()) <= 2
+    assert float(out[0].min()) == 0.0 and float(out[0].max()) < 1e5        # background zeroed in place, as upstream
+    both = mg & mo
+    assert gu.rel(out[0][both], ref[0][both]) < 1e-5
+    # compare normals where the 3x3 neighbourhood has the same silhouette in both (a flipped neighbour changes the stencil)
+    agree = (mg == mo).float()[None, None]
+    safe = torch.nn.functional.avg_pool2d(agree, 3, stride=1, padding=1)[0, 0] > 0.999
+    assert int(safe.sum()) > 0.8 * hw[0] * hw[1]
+    assert float((out[1] - ref[1])[safe].abs().max()) < 2e-3
+    assert float(out[1][~mg].abs().max()) == 0.0
+
+
 def test_api_errors():
     dec = gu.gpu_decoder("B")
     K, R, T = cases.camera(("front", 1.6), (16, 16))
@@ -310,8 +335,6 @@ def test_api_errors():
     lat = cases.synth.make_latent().cuda()
     with pytest.raises(NotImplementedError):
         pkg.SDFRenderer(dec, K, img_hw=(16, 16), scale_list=[2, 1], march_step_list=[3, -1]).render(lat, R.cuda(), T.cuda())
-    with pytest.raises(NotImplementedError):
-        pkg.SDFRenderer(dec, K, img_hw=(16, 16), use_depth2normal=True).render(lat, R.cuda(), T.cuda())
     with pytest.raises(ValueError):
         ren.render_depth(lat, R.cuda(), T.cuda(), ray_marching_type="bogus")
     with pytest.raises(RuntimeError):

@@ -75,6 +75,54 @@ def test_oracle_matches_live_reference(name):
         assert _rel(b[i].detach(), a[i]) < 1e-6
 
 
+@pytest.mark.skipif(not ref_shim.available(), reason="reference tree not present (GPU box)")
+def test_depth2normal_matches_live_reference():
+    """use_depth2normal (renderer.py:972-975): the oracle's restatement and the product's host-side mirror
+    (device-agnostic PyTorch, so checked here on CPU) against the reference's own function, bit for bit, including the
+    in-place zeroing of the background of the depth map; then the whole render() branch, oracle vs reference."""
+    import importlib
+    import sys
+    import numpy as np
+    from oracle.sdf_oracle import depth2normal as d2n_oracle
+    Rmod, _, RefDecoder = ref_shim.load()
+    d2n_ref = sys.modules["core.utils.render_utils"].depth2normal
+    d2n_prod = importlib.import_module("dist-renderer_b200.render_utils").depth2normal
+    g = torch.Generator().manual_seed(3)
+    for (h, w) in [(7, 9), (40, 33), (3, 3), (2, 5), (1, 1)]:
+        d = torch.rand(h, w, generator=g) * 2 + 0.5
+        d[torch.rand(h, w, generator=g) < 0.3] = 1e11
+        d[0, 0] = 0.0
+        fx, fy = np.float32(57.6), np.float32(50.0)
+        da, db, dc = d.clone(), d.clone(), d.clone()
+        a, b, c = d2n_ref(da, fx, fy), d2n_oracle(db, fx, fy), d2n_prod(dc, fx, fy)
+        assert torch.equal(a, b) and torch.equal(a, c)
+        assert torch.equal(da, db) and torch.equal(da, dc) and float(da[0, 0]) == 0.0
+    # gradients w.r.t. the depth agree (the product forms the differences before scattering: last-bit differences)
+    d = torch.rand(12, 12, generator=g) + 0.5
+    d[2:4, 3] = 1e11
+    wgt = torch.randn(12, 12, 3, generator=g)
+    grads = []
+    for fn in (d2n_ref, d2n_oracle, d2n_prod):
+        x = d.clone().requires_grad_(True)
+        (fn(x * 1.0, np.float32(30.0)) * wgt).sum().backward()
+        grads.append(x.grad)
+    assert torch.equal(grads[0], grads[1]) and _rel(grads[2], grads[0]) < 1e-6
+    # the render() branch
+    cs = cases.CASES["trivial_40"]
+    dec = cases.decoder(cs["decoder"])
+    ref = RefDecoder(dec.latent_size, **cases.synth.STANDARD_SPEC).eval()
+    ref.load_state_dict(dec.state_dict())
+    K, R, T = cases.camera(cs["cam"], cs["hw"])
+    kw = dict(img_hw=cs["hw"], march_step=cs["march_step"], buffer_size=cs["buffer_size"], use_depth2normal=True)
+    a = Rmod.SDFRenderer(ref, K, use_gpu=False, **kw).render(cases.synth.make_latent(), R, T,
+                                                            ray_marching_type="recursive", no_grad=True)
+    b = OracleSDFRenderer(dec, K, **kw).render(cases.synth.make_latent(), R, T, ray_marching_type="recursive",
+                                               no_grad=True)
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+    assert float(a[0].min()) == 0.0 and float(a[0].max()) < 1e5      # background of the returned depth is 0, not 1e11
+
+
 def test_fp64_twin_noise_floor():
     """The fp64 twin bounds how far a faithful fp32 implementation may sit from the fp32 reference."""
     cs = cases.CASES["trivial_40"]
