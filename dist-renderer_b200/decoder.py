@@ -76,6 +76,9 @@ class Decoder(nn.Module):
     def layer(self, l):
         return getattr(self, "lin%d" % l)
 
+    def latent_size_regul(self, lat_vecs):  # deep_sdf_decoder.py:75-77
+        return lat_vecs.pow(2).mean(1)
+
     def inference(self, input):
         """Forward, rows = [latent | xyz] -> (K, 1)  (deep_sdf_decoder.py:80-111).
 
@@ -126,28 +129,35 @@ class Decoder(nn.Module):
         return self.inference(input)
 
 
-def load_decoder(experiment_directory, checkpoint_num=None, parallel=False):
-    """specs.json + ModelParameters/<ckpt>.pth loader, after decoder_utils.py:7-51 (SDF decoder only).
+def load_decoder(experiment_directory, checkpoint_num=None, color_size=None, experiment_directory_color=None,
+                 parallel=True):
+    """specs.json + ModelParameters/<ckpt>.pth loader with the reference's signature (decoder_utils.py:7-51).
 
-    The reference wraps the module in DataParallel purely so that the ``module.`` key prefix of the saved
-    state dict matches; here the prefix is stripped instead and a bare module is returned.  ``parallel=True``
-    returns an object with a ``.module`` attribute for call sites written as ``load_decoder(...).module``.
+    * SDF decoder (``color_size=None``): ``Decoder(CodeLength, **NetworkSpecs)``, weights from
+      ``<experiment_directory>/ModelParameters/<checkpoint_num>.pth`` (keys carry the ``module.`` prefix of the
+      DataParallel wrapper they were saved from).
+    * colour decoder (``color_size=k``): latent = shape code + colour code (``CodeLength + k``), ``dims[3] += k`` so the
+      ``latent_in`` concatenation still adds up, ``last_dim=3``; weights from ``experiment_directory_color`` (saved
+      without the prefix).
+    ``parallel=True`` (the reference's default) returns the module wrapped in ``torch.nn.DataParallel`` -- call sites are
+    written ``load_decoder(...).module.cuda()``; ``parallel=False`` returns the bare module.
     """
     specs_filename = os.path.join(experiment_directory, "specs.json")
     if not os.path.isfile(specs_filename):
         raise Exception('The experiment directory does not include specifications file "specs.json"')
-    specs = json.load(open(specs_filename))
-    decoder = Decoder(specs["CodeLength"], **specs["NetworkSpecs"])
+    with open(specs_filename) as f:
+        specs = json.load(f)
+    net = dict(specs["NetworkSpecs"])
+    latent_size = specs["CodeLength"]
+    if color_size is not None:
+        net["dims"] = list(net["dims"])
+        net["dims"][3] = net["dims"][3] + color_size
+        latent_size = latent_size + color_size
+        net["last_dim"] = 3
+    decoder = Decoder(latent_size, **net)
     if checkpoint_num is not None:
-        saved = torch.load(os.path.join(experiment_directory, "ModelParameters", checkpoint_num + ".pth"),
-                           map_location="cpu")
-        sd = {(k[len("module."):] if k.startswith("module.") else k): v
-              for k, v in saved["model_state_dict"].items()}
+        src = experiment_directory_color if color_size is not None else experiment_directory
+        saved = torch.load(os.path.join(src, "ModelParameters", checkpoint_num + ".pth"), map_location="cpu")
+        sd = {(k[len("module."):] if k.startswith("module.") else k): v for k, v in saved["model_state_dict"].items()}
         decoder.load_state_dict(sd)
-    if parallel:
-        class _Wrap:
-            pass
-        w = _Wrap()
-        w.module = decoder
-        return w
-    return decoder
+    return torch.nn.DataParallel(decoder) if parallel else decoder

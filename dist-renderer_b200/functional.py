@@ -104,3 +104,21 @@ def decode_sdf_gradient(decoder, latent_vector, points, clamp_dist=0.1, MAX_POIN
     if n > 0:
         _abi.check(lib.dist_decoder_input_grad(net, eng, _abi.ptr(pts), n, None, cd, _abi.ptr(grad), None, st))
     return grad
+
+
+def decode_color(decoder, color_code, shape_code, points, MAX_POINTS=100000, no_grad=False):
+    """rgb (K,3) of `points` (K,3) from a colour decoder fed [shape code | colour code | xyz] rows --
+    decoder_utils.py:94-112 (used by SDFRenderer_color, renderer_rgb.py:33).
+
+    The colour network (``last_dim = 3``) is evaluated once per hit pixel after the march (about 1e-3 of the decoder
+    rows of a render), through the module's generic PyTorch layers: the fused engines cover the single-output SDF
+    network.  Rows go through in chunks of MAX_POINTS like upstream, so the GEMM shapes -- and with them the last bits
+    of the result -- are the reference's."""
+    n = points.shape[0]
+    chunks = []
+    for start in range(0, max(n, 1), MAX_POINTS):
+        end = min(start + MAX_POINTS, n)
+        inputs = torch.cat([shape_code.expand(end - start, -1), color_code.expand(end - start, -1), points[start:end]], 1)
+        color = decoder.inference(inputs)
+        chunks.append(color.detach() if no_grad else color)
+    return torch.cat(chunks, 0)

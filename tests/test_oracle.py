@@ -123,6 +123,59 @@ def test_depth2normal_matches_live_reference():
     assert float(a[0].min()) == 0.0 and float(a[0].max()) < 1e5      # background of the returned depth is 0, not 1e11
 
 
+_SMALL_SPEC = dict(dims=[64] * 8, dropout=list(range(8)), dropout_prob=0.2, norm_layers=list(range(8)), latent_in=[4],
+                   xyz_in_all=False, use_tanh=False, latent_dropout=False, weight_norm=True)
+
+
+def _write_experiment(root, make_decoder):
+    """An experiment directory in the upstream DeepSDF layout: specs.json, an SDF checkpoint saved from a DataParallel
+    wrapper (keys prefixed `module.`) and a colour checkpoint saved without the prefix (decoder_utils.py:33-41)."""
+    import json
+    import os
+    json.dump({"NetworkArch": "deep_sdf_decoder", "CodeLength": 16, "NetworkSpecs": _SMALL_SPEC},
+              open(os.path.join(root, "specs.json"), "w"))
+    col = os.path.join(root, "color")
+    os.makedirs(os.path.join(root, "ModelParameters"))
+    os.makedirs(os.path.join(col, "ModelParameters"))
+    torch.manual_seed(0)
+    sdf = torch.nn.DataParallel(make_decoder(16, **_SMALL_SPEC))
+    torch.save({"epoch": 1, "model_state_dict": sdf.state_dict()}, os.path.join(root, "ModelParameters", "latest.pth"))
+    cspec = dict(_SMALL_SPEC, dims=[64, 64, 64, 72, 64, 64, 64, 64])
+    torch.save({"epoch": 1, "model_state_dict": make_decoder(24, last_dim=3, **cspec).state_dict()},
+               os.path.join(col, "ModelParameters", "latest.pth"))
+    return col
+
+
+def test_load_decoder_roundtrip(tmp_path):
+    """load_decoder (decoder_utils.py:7-51): SDF and colour decoders, DataParallel wrapper by default."""
+    col = _write_experiment(str(tmp_path), cases.pkg.Decoder)
+    wrapped = cases.pkg.load_decoder(str(tmp_path), "latest")
+    assert isinstance(wrapped, torch.nn.DataParallel) and wrapped.module.latent_size == 16
+    bare = cases.pkg.load_decoder(str(tmp_path), "latest", parallel=False)
+    x = torch.randn(9, 19)
+    assert torch.equal(wrapped.module.eval().inference(x), bare.eval().inference(x))
+    colour = cases.pkg.load_decoder(str(tmp_path), "latest", color_size=8, experiment_directory_color=col).module.eval()
+    assert colour.latent_size == 24 and colour.lin3.weight_v.shape[0] == 72 - 27 and colour.lin8.out_features == 3
+    rgb = cases.pkg.decode_color(colour, torch.randn(1, 8), torch.randn(1, 16), torch.randn(70, 3), MAX_POINTS=32)
+    assert rgb.shape == (70, 3) and float(rgb.abs().max()) <= 1.0
+    with pytest.raises(Exception):
+        cases.pkg.load_decoder(str(tmp_path / "nowhere"))
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="reference tree not present (GPU box)")
+def test_load_decoder_and_decode_color_match_live_reference(tmp_path):
+    _, DU, RefDecoder = ref_shim.load()
+    col = _write_experiment(str(tmp_path), RefDecoder)
+    a = DU.load_decoder(str(tmp_path), "latest").module.eval()
+    b = cases.pkg.load_decoder(str(tmp_path), "latest").module.eval()
+    x = torch.randn(50, 19)
+    assert torch.equal(a.inference(x), b.inference(x))
+    ac = DU.load_decoder(str(tmp_path), "latest", color_size=8, experiment_directory_color=col).module.eval()
+    bc = cases.pkg.load_decoder(str(tmp_path), "latest", color_size=8, experiment_directory_color=col).module.eval()
+    pts, sc, cc = torch.randn(70, 3), torch.randn(1, 16), torch.randn(1, 8)
+    assert torch.equal(DU.decode_color(ac, cc, sc, pts, MAX_POINTS=32), cases.pkg.decode_color(bc, cc, sc, pts, MAX_POINTS=32))
+
+
 def test_fp64_twin_noise_floor():
     """The fp64 twin bounds how far a faithful fp32 implementation may sit from the fp32 reference."""
     cs = cases.CASES["trivial_40"]
