@@ -66,6 +66,21 @@ def make_decoder(kind="B", latent_size=256, width=512, depth=8, latent_in=4, see
     return dec.eval()
 
 
+def make_color_decoder(latent_size=256, color_size=8, seed=5):
+    """Colour network of `load_decoder(color_size=...)` (decoder_utils.py:15-24): latent = shape + colour code,
+    dims[3] widened by color_size, three outputs; seeded default init (any smooth rgb field serves the tests)."""
+    spec = dict(STANDARD_SPEC)
+    spec["dims"] = list(spec["dims"])
+    spec["dims"][3] = spec["dims"][3] + color_size
+    state = torch.random.get_rng_state()
+    torch.manual_seed(seed)
+    try:
+        dec = Decoder(latent_size + color_size, last_dim=3, **spec)
+    finally:
+        torch.random.set_rng_state(state)
+    return dec.eval()
+
+
 def make_latent(latent_size=256, seed=1, std=0.1):
     g = torch.Generator().manual_seed(seed)
     return std * torch.randn(1, latent_size, generator=g)

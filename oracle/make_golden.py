@@ -28,7 +28,32 @@ def ref_decoder(dec):
     return ref
 
 
+def color_fixture():
+    """tests/golden/color_24.npz from the reference's SDFRenderer_color.render (core/sdfrenderer/renderer_rgb.py:70)."""
+    _, _, RefDecoder = ref_shim.load()
+    Color = ref_shim.load_color()
+    dec, col = cases.decoder("B"), cases.synth.make_color_decoder()
+    spec = dict(cases.synth.STANDARD_SPEC, dims=list(col.dims[1:-1]))
+    ref_col = RefDecoder(col.latent_size, last_dim=3, **spec).eval()
+    ref_col.load_state_dict(col.state_dict())
+    hw, K, R, T, cc, lights, energies = cases.color_case()
+    ren = Color(ref_decoder(dec), ref_col, K, img_hw=hw, use_gpu=False)
+    lat = cases.synth.make_latent().requires_grad_(True)
+    ccg = cc.clone().requires_grad_(True)
+    out = ren.render(ccg, lat, R, T, lighting_locations=lights, lighting_energies=energies)
+    (out[2].sum() + out[0][out[3].bool()].sum()).backward()
+    plain = ren.render(cc, cases.synth.make_latent(), R, T, no_grad=True)
+    np.savez_compressed(os.path.join(cases.GOLDEN_DIR, "color_24.npz"), depth=out[0].detach().numpy(),
+                        normal=out[1].detach().numpy(), color=out[2].detach().numpy(), mask=out[3].numpy(),
+                        min_sdf=out[4].detach().numpy(), color_unlit=plain[2].numpy(), g_latent=lat.grad.numpy(),
+                        g_color=ccg.grad.numpy(), weights_checksum=cases.weights_checksum(col))
+    print("color_24 hits", int(out[3].sum()), "max rgb", float(out[2].abs().max()))
+
+
 def main():
+    if "--color-only" in sys.argv:      # adds the colour fixture without rewriting the others
+        os.makedirs(cases.GOLDEN_DIR, exist_ok=True)
+        return color_fixture()
     Rmod, DU, _ = ref_shim.load()
     os.makedirs(cases.GOLDEN_DIR, exist_ok=True)
     lat0 = cases.synth.make_latent()
@@ -72,6 +97,7 @@ def main():
                         normal1=out[7].detach().numpy(), depth1=out[8].detach().numpy(),
                         weights_checksum=cases.weights_checksum(dec))
     print("warp_40 loss", float(out[0]))
+    color_fixture()
 
 
 if __name__ == "__main__":

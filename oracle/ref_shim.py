@@ -83,6 +83,17 @@ def load_warp():
     return _loaded["W"]
 
 
+def load_color():
+    """Returns the reference's SDFRenderer_color class (core/sdfrenderer/renderer_rgb.py), CPU-runnable."""
+    if "C" in _loaded:
+        return _loaded["C"]
+    R, _, _ = load()
+    sys.modules["renderer"] = R                      # renderer_rgb.py:5 does `from renderer import SDFRenderer`
+    C = _load("core.sdfrenderer.renderer_rgb", "core/sdfrenderer/renderer_rgb.py")
+    _loaded["C"] = C.SDFRenderer_color
+    return _loaded["C"]
+
+
 def load_create_mesh():
     """The reference's core/evaluation/create_mesh.py with skimage / plyfile stubbed (absent here; only the sampling
     half is exercised), `.cuda()` / `.cpu()` round trips neutralised and the torch>=1.6 true-division of

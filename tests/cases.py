@@ -70,6 +70,15 @@ def weights_checksum(dec):
         return float(sum(p.double().abs().sum() for p in dec.state_dict().values()))
 
 
+def color_case():
+    """next-3: SDFRenderer_color on a 24x24 front view, 8-d colour code, one point light with energy 0.8."""
+    hw = (24, 24)
+    K, R, T = camera(("front", 1.6), hw)
+    g = torch.Generator().manual_seed(13)
+    color_code = 0.1 * torch.randn(1, 8, generator=g)
+    return hw, K, R, T, color_code, torch.tensor([[0.5, 1.0, -3.0]]), torch.tensor([0.8])
+
+
 def warp_case():
     """Two views 15 degrees apart on the ring + two seeded random images (config 4's origin: render_warp)."""
     H = W = 40

@@ -176,6 +176,57 @@ def test_load_decoder_and_decode_color_match_live_reference(tmp_path):
     assert torch.equal(DU.decode_color(ac, cc, sc, pts, MAX_POINTS=32), cases.pkg.decode_color(bc, cc, sc, pts, MAX_POINTS=32))
 
 
+def _color_setup():
+    from oracle.color_oracle import OracleColorRenderer
+    hw, K, R, T, cc, lights, energies = cases.color_case()
+    col = cases.synth.make_color_decoder()
+    ora = OracleColorRenderer(cases.decoder("B"), col, K, img_hw=hw)
+    return ora, col, (hw, K, R, T, cc, lights, energies)
+
+
+def test_color_oracle_matches_golden():
+    """next-3: oracle/color_oracle.py vs the reference's SDFRenderer_color.render outputs in tests/golden/color_24.npz."""
+    import numpy as np
+    ora, col, (hw, K, R, T, cc, lights, energies) = _color_setup()
+    gold = np.load(os.path.join(cases.GOLDEN_DIR, "color_24.npz"))
+    assert abs(cases.weights_checksum(col) - float(gold["weights_checksum"])) < 1e-6 * float(gold["weights_checksum"])
+    lat, ccg = cases.synth.make_latent().requires_grad_(True), cc.clone().requires_grad_(True)
+    out = ora.render(ccg, lat, R, T, lighting_locations=lights, lighting_energies=energies)
+    (out[2].sum() + out[0][out[3].bool()].sum()).backward()
+    assert int((out[3].numpy() != gold["mask"]).sum()) == 0
+    for i, key in ((0, "depth"), (1, "normal"), (2, "color"), (4, "min_sdf")):
+        assert _rel(out[i].detach(), torch.from_numpy(gold[key])) < 1e-6, key
+    assert _rel(lat.grad, torch.from_numpy(gold["g_latent"])) < 1e-5
+    assert _rel(ccg.grad, torch.from_numpy(gold["g_color"])) < 1e-5
+    plain = ora.render(cc, cases.synth.make_latent(), R, T, no_grad=True)
+    assert _rel(plain[2], torch.from_numpy(gold["color_unlit"])) < 1e-6
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="reference tree not present (GPU box)")
+def test_color_oracle_matches_live_reference():
+    """Bit-for-bit against renderer_rgb.py run through the shim: outputs, and gradients w.r.t. both codes."""
+    _, _, RefDecoder = ref_shim.load()
+    Color = ref_shim.load_color()
+    ora, col, (hw, K, R, T, cc, lights, energies) = _color_setup()
+    dec = cases.decoder("B")
+    ref_sdf = RefDecoder(dec.latent_size, **cases.synth.STANDARD_SPEC).eval()
+    ref_sdf.load_state_dict(dec.state_dict())
+    ref_col = RefDecoder(col.latent_size, last_dim=3, **dict(cases.synth.STANDARD_SPEC, dims=list(col.dims[1:-1]))).eval()
+    ref_col.load_state_dict(col.state_dict())
+    ren = Color(ref_sdf, ref_col, K, img_hw=hw, use_gpu=False)
+    lat = cases.synth.make_latent()
+    for kw in (dict(), dict(lighting_locations=lights), dict(lighting_locations=lights, lighting_energies=energies)):
+        a, b = ren.render(cc, lat, R, T, no_grad=True, **kw), ora.render(cc, lat, R, T, no_grad=True, **kw)
+        assert all(torch.equal(x, y) for x, y in zip(a, b))
+    grads = []
+    for r in (ren, ora):
+        l, c = lat.clone().requires_grad_(True), cc.clone().requires_grad_(True)
+        o = r.render(c, l, R, T, lighting_locations=lights)
+        (o[2].sum() + o[0][o[3].bool()].sum()).backward()
+        grads.append((l.grad, c.grad))
+    assert torch.equal(grads[0][0], grads[1][0]) and torch.equal(grads[0][1], grads[1][1])
+
+
 def test_fp64_twin_noise_floor():
     """The fp64 twin bounds how far a faithful fp32 implementation may sit from the fp32 reference."""
     cs = cases.CASES["trivial_40"]
