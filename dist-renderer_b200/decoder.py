@@ -94,6 +94,8 @@ class Decoder(nn.Module):
 
     def _inference_fused(self, input):
         from .functional import decode_sdf
+        if self.dims[-1] != 1:          # colour networks (last_dim = 3) are not covered by the fused engines
+            return None
         L = self.latent_size
         lat = input[:1, :L]
         if L > 0 and not bool((input[:, :L] == lat).all()):

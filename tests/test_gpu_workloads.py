@@ -183,6 +183,40 @@ def test_profile_window_counts_decoder_launches():
     assert n.value == 0 and ms.value == 0.0
 
 
+def test_color_renderer_matches_oracle():
+    """next-3: SDFRenderer_color (depth / normal / silhouette from the CUDA tracer, colour network + point-light shading
+    on the hit pixels) vs oracle/color_oracle.py, which is pinned bit for bit to the reference's renderer_rgb.py."""
+    from oracle.color_oracle import OracleColorRenderer
+    hw, K, R, T, cc, lights, energies = cases.color_case()
+    col = synth.make_color_decoder()
+    ora = OracleColorRenderer(cases.decoder("B"), col, K, img_hw=hw)
+    ren = pkg.SDFRenderer_color(gu.gpu_decoder("B"), copy.deepcopy(col).cuda(), K, img_hw=hw)
+    lat = synth.make_latent()
+    for lit in (False, True):
+        kc = dict(lighting_locations=lights, lighting_energies=energies) if lit else {}
+        kg = {k: v.cuda() for k, v in kc.items()}
+        ref = ora.render(cc, lat, R, T, no_grad=True, **kc)
+        out = [t.cpu() for t in ren.render(cc.cuda(), lat.cuda(), R.cuda(), T.cuda(), no_grad=True, **kg)]
+        assert [tuple(t.shape) for t in out] == [hw, hw + (3,), hw + (3,), hw, hw] and out[3].dtype == torch.uint8
+        mg, mo = out[3].bool(), ref[3].bool()
+        assert int((mg != mo).sum()) <= 2
+        both = mg & mo
+        assert gu.rel(out[0][both], ref[0][both]) < 1e-5 and gu.rel(out[4], ref[4]) < 1e-3
+        scale = float(ref[2].abs().max())
+        bad = ((out[2] - ref[2])[both].abs().max(-1)[0] > 2e-3 * scale).float().mean()
+        assert float(bad) <= 0.03                 # shading uses the normals: a ReLU-flip pixel is an outlier, not an error
+        assert float(out[2][~mg].abs().max()) == 0.0
+    l_c, c_c = lat.clone().requires_grad_(True), cc.clone().requires_grad_(True)
+    l_g, c_g = lat.cuda().requires_grad_(True), cc.cuda().requires_grad_(True)
+    o_c = ora.render(c_c, l_c, R, T)
+    o_g = ren.render(c_g, l_g, R.cuda(), T.cuda())
+    (o_c[2].sum() + o_c[0][o_c[3].bool()].sum()).backward()
+    (o_g[2].sum() + o_g[0][o_g[3].bool()].sum()).backward()
+    flips = int((o_g[3].cpu() != o_c[3]).sum())
+    assert gu.rel(c_g.grad.cpu(), c_c.grad) < (2e-3 if flips == 0 else 5e-2)
+    assert gu.rel(l_g.grad.cpu(), l_c.grad) < (2e-3 if flips == 0 else 5e-2)
+
+
 def test_render_warp_matches_oracle():
     """next-1: SDFRenderer_warp.render_warp (two-view reprojection + photometric L1) vs the pinned CPU restatement."""
     import importlib
