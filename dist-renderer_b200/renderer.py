@@ -7,13 +7,14 @@ launches on the current stream and chains the tiny camera Jacobian (c = -R^T T, 
 
 Differences from the reference, all loud:
   * no CPU path: ``use_gpu=False`` or a CPU decoder raises;
-  * ``sample_index_type != 'min_abs'`` raises NotImplementedError;
+  * ``sample_index_type != 'min_abs'`` raises NotImplementedError (no caller in the reference uses another type);
     ``pyramid_recursive`` is implemented for the default ``scale_list=[4,2,1]`` on full images;
   * 3x4 ``transform_matrix`` raises (the reference's own 3x4 inverse path calls an un-imported ``pdb``);
   * when no ray meets the unit sphere the reference dies inside ``.max()`` of an empty tensor; here
     ``ValueError('No valid depth.')`` (renderer.py:215) is raised;
   * new: ``render_silhouette`` = the (mask, min_abs_query) pair; ``rows=(row0, row_step, n_rows)`` renders a band
-    of image rows for ray-tile sharding across GPUs (parallel.py).
+    of image rows for ray-tile sharding across GPUs (parallel.py); ``render_views`` marches V poses of one shape in
+    one fused call.
 """
 import numpy as np
 import torch
