@@ -1,4 +1,4 @@
-"""CPU, gloo, world_size 2: the ray-tile sharding logic (band assignment, pack, ONE all-gather, unpack, gradient sum)."""
+"""CPU, gloo, world_size 2 and 3: the ray-tile sharding logic (band assignment, pack, ONE all-gather, unpack, gradient sum)."""
 import importlib
 import os
 import socket
@@ -47,18 +47,19 @@ def _worker(rank, world, port, H, W, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("hw", [(10, 7), (9, 5)])      # even split and ragged split (5 + 4 rows)
-def test_band_gather_world2(hw):
+# even split, ragged split (5 + 4 rows), three ranks with a ragged tail (4 + 3 + 3 rows)
+@pytest.mark.parametrize("world,hw", [(2, (10, 7)), (2, (9, 5)), (3, (10, 4))])
+def test_band_gather_multi_process(world, hw):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, hw[0], hw[1], q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, hw[0], hw[1], q)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=120) for _ in procs]
     for p in procs:
         p.join(timeout=60)
-    assert sorted(res) == [(0, True), (1, True)]
+    assert sorted(res) == [(r, True) for r in range(world)]
 
 
 def test_band_single_process():
