@@ -1,5 +1,5 @@
 """Timing of the other BASELINE.json configurations (not the headline bench): config 3 (224x224, march 100, buffer 3,
-fwd+bwd), config 4 (24 views 256x256 fwd+bwd, looped), config 2 variants (512x512 forward only, pyramid/trivial)."""
+fwd+bwd), config 4 (24 views 256x256 fwd+bwd, looped and as one fused march; see also tools/bench_views.py), config 2 variants (512x512 forward only, pyramid/trivial)."""
 import importlib, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -41,3 +41,9 @@ def multi():
     tot.backward()
 ms = timeit(multi, n=3)
 print("config4 24 views 256x256 fwd+bwd (looped): %.1f ms  %.3f M rays/s" % (ms, 24 * 65536 / ms / 1e3))
+Rs, Ts = torch.stack([r for r, _ in views]), torch.stack([t for _, t in views])
+def fused():
+    l = lat0.detach().requires_grad_(True)
+    bench.loss_of(ren.render_views(l, Rs, Ts, ray_marching_type="recursive")).backward()
+ms = timeit(fused, n=3)
+print("config4 24 views 256x256 fwd+bwd (one fused march): %.1f ms  %.3f M rays/s" % (ms, 24 * 65536 / ms / 1e3))
