@@ -94,6 +94,17 @@ def load_color():
     return _loaded["C"]
 
 
+def load_deepsdf():
+    """Returns the reference's SDFRenderer_deepsdf class (core/sdfrenderer/renderer_deepsdf.py), CPU-runnable."""
+    if "D" in _loaded:
+        return _loaded["D"]
+    R, _, _ = load()
+    sys.modules["renderer"] = R                      # renderer_deepsdf.py:5 does `from renderer import SDFRenderer`
+    D = _load("core.sdfrenderer.renderer_deepsdf", "core/sdfrenderer/renderer_deepsdf.py")
+    _loaded["D"] = D.SDFRenderer_deepsdf
+    return _loaded["D"]
+
+
 def load_create_mesh():
     """The reference's core/evaluation/create_mesh.py with skimage / plyfile stubbed (absent here; only the sampling
     half is exercised), `.cuda()` / `.cpu()` round trips neutralised and the torch>=1.6 true-division of

@@ -227,6 +227,52 @@ def test_color_oracle_matches_live_reference():
     assert torch.equal(grads[0][0], grads[1][0]) and torch.equal(grads[0][1], grads[1][1])
 
 
+@pytest.mark.skipif(not ref_shim.available(), reason="reference tree not present (GPU box)")
+def test_deepsdf_sampler_host_logic_matches_live_reference(monkeypatch):
+    """SDFRenderer_deepsdf.get_samples / get_freespace_samples (renderer_deepsdf.py:14-65).  The product methods are
+    device-agnostic host code around decode_sdf; here they run on CPU -- on a renderer object whose constructor (which
+    insists on a CUDA decoder) is bypassed and whose decoder calls are routed to the oracle's decode_sdf -- against the
+    reference class executed through the shim, bit for bit, including the random draws under a common seed."""
+    import importlib
+    import numpy as np
+    from oracle.sdf_oracle import decode_sdf as oracle_decode
+    Deep = ref_shim.load_deepsdf()
+    _, _, RefDecoder = ref_shim.load()
+    mod = importlib.import_module("dist-renderer_b200.renderer_deepsdf")
+    monkeypatch.setattr(mod.functional, "decode_sdf",
+                        lambda dec, lat, pts, clamp_dist=0.1, **kw: oracle_decode(dec, lat, pts, clamp_dist=clamp_dist))
+    hw = (24, 24)
+    K, R, T = cases.camera(("front", 1.6), hw)
+    dec = cases.decoder("B")
+    ref_dec = RefDecoder(dec.latent_size, **cases.synth.STANDARD_SPEC).eval()
+    ref_dec.load_state_dict(dec.state_dict())
+    lat = cases.synth.make_latent()
+    depth, normal, _, _ = OracleSDFRenderer(dec, K, img_hw=hw).render(lat, R, T, ray_marching_type="recursive",
+                                                                       no_grad=True)
+    RT = torch.cat([R, T[:, None]], 1)
+    ref = Deep(ref_dec, K, img_hw=hw, use_gpu=False)
+    prod = object.__new__(mod.SDFRenderer_deepsdf)            # no CUDA here: set what the camera helpers read
+    prod.decoder, prod.device, prod.img_hw, prod.rows, prod.Pv = dec, torch.device("cpu"), hw, (0, 1, hw[0]), hw[0] * hw[1]
+    prod.K_inv = torch.from_numpy(np.linalg.inv(K)).float()
+    prod.transform_matrix = torch.tensor([[1., 0., 0.], [0., 0., -1.], [0., 1., 0.]])
+    prod._homo_calib = prod._calib_map = None
+    a = ref.get_samples(lat, RT, depth.clone(), normal.clone(), use_rand=False)
+    b = prod.get_samples(lat, RT, depth.clone(), normal.clone(), use_rand=False)
+    assert a[0].numel() == int(((depth < 1e5) & (depth > 0)).sum()) > 50
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    assert float(a[0].detach().abs().max()) < 0.05 and float(a[1].detach().abs().max()) < 0.05   # near zero: the samples straddle the surface
+    for fn, args in (("get_samples", (depth.clone(), normal.clone())), ("get_freespace_samples", (depth.clone(),))):
+        torch.manual_seed(21)
+        x = getattr(ref, fn)(lat, RT, *args)
+        torch.manual_seed(21)
+        y = getattr(prod, fn)(lat, RT, *args)
+        x, y = (x, y) if isinstance(x, tuple) else ((x,), (y,))
+        assert all(torch.equal(p, q) for p, q in zip(x, y))
+    torch.manual_seed(3)
+    free = prod.get_freespace_samples(lat, RT, depth.clone(), number=3)
+    assert free.numel() == 3 * a[0].numel() and float(free.min()) > -0.05       # in front of the surface the sdf is positive
+
+
 def test_fp64_twin_noise_floor():
     """The fp64 twin bounds how far a faithful fp32 implementation may sit from the fp32 reference."""
     cs = cases.CASES["trivial_40"]
