@@ -9,6 +9,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libdist_b200.so")
 
+ABI_VERSION = 2
 MAX_LAYERS = 16
 MAX_WIDTH = 512
 MAX_BUFFER = 8
@@ -35,18 +36,20 @@ class Camera(C.Structure):
     _fields_ = [("Kinv", C.c_float * 9), ("M", C.c_float * 9), ("Mn", C.c_float * 9), ("R", C.c_void_p),
                 ("cam_pos", C.c_void_p),
                 ("width", C.c_int32), ("height", C.c_int32), ("row0", C.c_int32), ("row_step", C.c_int32),
-                ("n_rows", C.c_int32), ("radius", C.c_float), ("n_views", C.c_int32)]
+                ("n_rows", C.c_int32), ("radius", C.c_float), ("n_views", C.c_int32), ("row_group", C.c_int32)]
 
 
 class March(C.Structure):
     _fields_ = [("march_step", C.c_int32), ("buffer_size", C.c_int32), ("marching_type", C.c_int32),
                 ("first_query_check", C.c_int32), ("ratio", C.c_float), ("threshold", C.c_float),
-                ("clamp_dist", C.c_float), ("replay_grad_rounding", C.c_int32), ("coarse_steps", C.c_int32 * 2)]
+                ("clamp_dist", C.c_float), ("replay_grad_rounding", C.c_int32), ("coarse_steps", C.c_int32 * 2),
+                ("screen", C.c_int32), ("screen_margin", C.c_float), ("screen_tpred", C.c_float),
+                ("cam_grad_levels", C.c_int32)]
 
 
 WS_FIELDS = ["ray", "entry", "exit_", "dist", "z", "flags", "nreal", "top_sdf", "top_pt", "top_zafter", "top_zgen",
              "list_a", "list_b", "pts", "sdf", "counts", "sdf_origin", "entry0", "top_lvl", "pyr_f", "pyr_i", "pyr_b",
-             "view_stat"]
+             "tile_mode", "seg_approx", "rq_idx", "rq_pts", "rq_sdf", "rq_cnt", "tile_counters", "view_stat"]
 
 
 class Workspace(C.Structure):
@@ -64,6 +67,8 @@ PROTOTYPES = {
     "dist_fold_latent": (C.c_int, [C.POINTER(Net), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dist_decoder_forward": (C.c_int, [C.POINTER(Net), C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_float,
                                        C.c_void_p, C.c_void_p]),
+    "dist_decoder_forward_tiers": (C.c_int, [C.POINTER(Net), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_float,
+                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dist_decoder_input_grad": (C.c_int, [C.POINTER(Net), C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_float,
                                           C.c_void_p, C.c_void_p, C.c_void_p]),
     "dist_decoder_backward": (C.c_int, [C.POINTER(Net), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
@@ -92,7 +97,7 @@ def lib():
         for name, (res, args) in PROTOTYPES.items():
             fn = getattr(L, name)  # AttributeError if the symbol is missing
             fn.restype, fn.argtypes = res, args
-        if L.dist_abi_version() != 1:
+        if L.dist_abi_version() != ABI_VERSION:
             raise DistError("libdist_b200.so ABI version mismatch")
         _lib = L
     return _lib

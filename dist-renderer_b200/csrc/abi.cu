@@ -165,6 +165,19 @@ int dist_decoder_forward(const dist_net_t* net, int engine, const float* points,
   return mlp_launch(net, nd, engine, 0, a, (cudaStream_t)stream);
 }
 
+int dist_decoder_forward_tiers(const dist_net_t* net, const float* points, int64_t n_host, const int32_t* n_dev,
+                               const uint8_t* tile_mode, float screen_thresh, float* sdf, uint8_t* seg_approx,
+                               unsigned long long* tile_counters, void* stream) {
+  NetDev nd;
+  int rc = make_netdev(net, &nd);
+  if (rc) return rc;
+  DIST_REQUIRE(tile_mode && seg_approx, "decoder_forward_tiers: tile_mode and seg_approx are required");
+  MlpArgs a{};
+  a.points = points; a.n_host = n_host; a.n_dev = n_dev; a.clamp_dist = 0.f; a.sdf = sdf;
+  a.tile_mode = tile_mode; a.screen_thresh = screen_thresh; a.seg_approx = seg_approx; a.tile_counters = tile_counters;
+  return mlp_launch(net, nd, DIST_ENGINE_TC, 0, a, (cudaStream_t)stream);
+}
+
 int dist_decoder_input_grad(const dist_net_t* net, int engine, const float* points, int64_t n_host,
                             const int32_t* n_dev, float clamp_dist, float* grad, float* sdf, void* stream) {
   NetDev nd;

@@ -53,6 +53,12 @@ struct MlpArgs {
   float* acc0;              // [N0] or null
   float* accl;              // [Nl] or null
   int64_t* rows_evaluated;  // optional counter (+= n)
+  // two-tier precision of forward launches on the tensor-core engine (mlp_tc.cu); all null / 0: full precision everywhere
+  const uint8_t* tile_mode; // [ceil(n/128)] 0 = evaluate the 128-row tile with one fp16 pass first, != 0 = three passes
+  float screen_thresh;      // one-pass values stand where every row of the 64-row half-tile has |sdf| > screen_thresh
+  int exact_last;           // never screen the tile that holds the last row
+  uint8_t* seg_approx;      // [ceil(n/64)] out: 1 = this half-tile's sdf are one-pass values
+  unsigned long long* tile_counters;  // optional [2]: tile programs evaluated with one / with three passes
 };
 int mlp_simt_launch(const NetDev& net, int mode, const MlpArgs& a, cudaStream_t stream);
 int mlp_tc_launch(const dist_net_t* net, const NetDev& nd, int mode, const MlpArgs& a, cudaStream_t stream);

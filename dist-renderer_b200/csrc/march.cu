@@ -19,14 +19,15 @@ struct Cam {
   float Kinv[9], M[9], Mn[9];
   const float* R;      // [n_views][9]
   const float* c;      // [n_views][3]
-  int W, H, row0, row_step, n_rows;
+  int W, H, row0, row_step, n_rows, row_group;   // local row l is image row row0 + (l / row_group) * row_step + l % row_group
   int n_views, Pv;     // views rendered by this call, pixels per view (W * n_rows); global pixel lp = v * Pv + lpv
   float radius;
 };
 
 // per-view bookkeeping of a multi-view call (ws.view_stat, [n_views][4] int32): live rays at step 0, executed march
 // steps (renderer.py:562 breaks per render, i.e. per view), float bits of the coarsest level's largest sphere entry
-enum { VS_LIVE0 = 0, VS_STEPS = 1, VS_MAXENTRY = 2, VS_STRIDE = 4 };
+enum { LVL_APPROX = 0x80, LVL_REQUERIED = 0x40 };   // flag bits of ws.top_lvl (bits 0-1: pyramid level)
+enum { VS_LIVE0 = 0, VS_STEPS = 1, VS_MAXENTRY = 2, VS_NONFINITE = 3, VS_STRIDE = 4 };
 
 __device__ __forceinline__ void load_view(const Cam& cam, int v, float (&R)[9], float (&c)[3]) {
 #pragma unroll
@@ -70,9 +71,13 @@ __device__ __forceinline__ void coord_ray(const Cam& cam, const float* R, float 
 #pragma unroll
   for (int i = 0; i < 3; ++i) ray[i] = v[i] / nrm;
 }
+// image row of local row l of this call's band (interleaved groups of row_group rows)
+__device__ __forceinline__ int global_row(const Cam& cam, int l) {
+  return cam.row0 + (l / cam.row_group) * cam.row_step + (l % cam.row_group);
+}
 // lpv: pixel index inside its view
 __device__ __forceinline__ void pixel_ray(const Cam& cam, const float* R, int lpv, float (&ray)[3]) {
-  coord_ray(cam, R, (float)(lpv % cam.W), (float)(cam.row0 + (lpv / cam.W) * cam.row_step), ray);
+  coord_ray(cam, R, (float)(lpv % cam.W), (float)global_row(cam, lpv / cam.W), ray);
 }
 
 // unit-sphere geometry of one ray (renderer.py:225-282): distance to the origin, hit flag, entry and exit depth
@@ -137,10 +142,25 @@ __device__ __forceinline__ void point_on_ray(const Cam& cam, const float (&c)[3]
 __device__ __forceinline__ float clampf(float v, float c) { return fminf(fmaxf(v, -c), c); }
 
 // ---------------------------------------------------------------------------------------------- set-up
+// Thread -> pixel assignment of the set-up kernel: 16 x 8 pixel blocks, blocks row-major, view-major.  The initial active
+// list (and, since compaction keeps the order, every later one) is therefore sorted by 2-D block, so a 128-row decoder
+// tile holds one compact image patch: its rays are all far from the surface or all near it much more often than a
+// 128-pixel strip of an image row -- which is what the two-tier precision of the decoder tiles (dist_march_t.screen) lives on.
+constexpr int BLK_W = 16, BLK_H = 8;
+__host__ __device__ inline int setup_threads_per_view(int W, int n_rows) {
+  return ((W + BLK_W - 1) / BLK_W) * ((n_rows + BLK_H - 1) / BLK_H) * (BLK_W * BLK_H);
+}
+
 __global__ void k_setup(Cam cam, dist_march_t mp, dist_workspace_t ws, float* Zdepth, uint8_t* mask, float* min_sdf,
                         int P, Level L1, Level L2) {
-  const int lp = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool in = lp < P;
+  const int tpv = setup_threads_per_view(cam.W, cam.n_rows);
+  const int gi = blockIdx.x * blockDim.x + threadIdx.x;
+  const int vv = gi / tpv, r = gi - vv * tpv;
+  const int wb = (cam.W + BLK_W - 1) / BLK_W;
+  const int blk = r / (BLK_W * BLK_H), inb = r % (BLK_W * BLK_H);
+  const int bx = (blk % wb) * BLK_W + inb % BLK_W, by = (blk / wb) * BLK_H + inb / BLK_W;
+  const bool in = vv < cam.n_views && bx < cam.W && by < cam.n_rows;
+  const int lp = in ? vv * cam.Pv + by * cam.W + bx : 0;
   const bool pyr = mp.marching_type == DIST_MARCH_PYRAMID;
   float R[9], c[3] = {0.f, 0.f, 0.f};
   const int v = in ? lp / cam.Pv : 0, lpv = lp - v * cam.Pv;
@@ -224,7 +244,8 @@ __global__ void k_pyr_rays(Cam cam, Level L, const uint8_t* fine_hit, int fine_w
   bool ownhit;
   load_view(cam, v, R, c);
   const float off = ((float)L.scale - 1.f) / 2.f;
-  coord_ray(cam, R, (float)L.scale * (float)ix + off, (float)L.scale * (float)iy + off, ray);
+  // the L.scale fine rows pooled into coarse row iy are consecutive image rows (row_group is a multiple of 4 on bands)
+  coord_ray(cam, R, (float)L.scale * (float)ix + off, (float)global_row(cam, L.scale * iy) + off, ray);
   sphere_geom(c, ray, cam.radius, dist, ownhit, entry, ex);
   L.ray[i] = ray[0]; L.ray[L.P + i] = ray[1]; L.ray[2 * L.P + i] = ray[2];
   bool pooled = false;
@@ -239,6 +260,21 @@ __global__ void k_pyr_rays(Cam cam, Level L, const uint8_t* fine_hit, int fine_w
   // (renderer.py:270-272); stash the own entry, resolve after the max is known
   L.start[i] = ownhit ? entry : -1.f;
   if (view_stat && ownhit) atomicMax(view_stat + VS_STRIDE * v + VS_MAXENTRY, __float_as_int(fmaxf(entry, 0.f)));
+}
+
+// Row bands: the fill value of renderer.py:270-272 is the largest sphere entry over the coarsest level of the WHOLE image,
+// not of this rank's band.  Geometry only (no decoder rows): every rank evaluates the full 1/4-resolution grid.
+__global__ void k_pyr_global_maxentry(Cam cam, int w2, int h2, int32_t* view_stat) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = w2 * h2;
+  if (i >= n * cam.n_views) return;
+  const int v = i / n, il = i - v * n;
+  float R[9], c[3], ray[3], dist, entry, ex;
+  bool hit;
+  load_view(cam, v, R, c);
+  coord_ray(cam, R, 4.f * (float)(il % w2) + 1.5f, 4.f * (float)(il / w2) + 1.5f, ray);
+  sphere_geom(c, ray, cam.radius, dist, hit, entry, ex);
+  if (hit) atomicMax(view_stat + VS_STRIDE * v + VS_MAXENTRY, __float_as_int(fmaxf(entry, 0.f)));
 }
 
 // start depth of a coarse level + its (fixed) active list and first query points
@@ -299,8 +335,15 @@ __global__ void k_append_origin(dist_workspace_t ws, int slot_total) {
 }
 
 // ---------------------------------------------------------------------------------------------- one march step
-__global__ void k_march_update(Cam cam, dist_march_t mp, dist_workspace_t ws, int step, int P) {
+// two-tier precision bookkeeping (dist_march_t.screen): `tiles` = capacity of one hint array (ws.tile_mode is [3][tiles])
+__global__ void k_march_update(Cam cam, dist_march_t mp, dist_workspace_t ws, int step, int P, int tiles) {
   const int n = ws.counts[step];
+  const bool scr = ws.seg_approx != nullptr;
+  uint8_t* hint_next = scr ? ws.tile_mode + (size_t)((step + 1) % 3) * tiles : nullptr;   // read by the next decoder launch
+  if (scr) {   // the array after next is free: clear it for the update kernel of the next step
+    uint8_t* clr = ws.tile_mode + (size_t)((step + 2) % 3) * tiles;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < tiles; j += gridDim.x * blockDim.x) clr[j] = 0;
+  }
   const int32_t* cur = (step & 1) ? ws.list_b : ws.list_a;
   int32_t* nxt = (step & 1) ? ws.list_a : ws.list_b;
   const float* pts_cur = ws.pts + (size_t)(step & 1) * (size_t)(P + 1) * 3;       // points of this step
@@ -309,7 +352,7 @@ __global__ void k_march_update(Cam cam, dist_march_t mp, dist_workspace_t ws, in
   const int B = mp.buffer_size;
   for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
     const int i = base + threadIdx.x;
-    bool live = false;
+    bool live = false, approx = false, near_pred = false;
     int lp = 0, v = -1;
     float znew = 0.f, entry = 0.f;
     if (i < n) {
@@ -324,9 +367,14 @@ __global__ void k_march_update(Cam cam, dist_march_t mp, dist_workspace_t ws, in
       ws.nreal[lp] = step + 1;
       if (step == 0 && sdf > mp.threshold) ws.flags[lp] |= 2;  // renderer.py:581
       const float asdf = fabsf(sdf);
+      approx = scr && ws.seg_approx[i >> 6] != 0;   // one-pass value: |sdf| > clamp + margin is all that is known exactly
+      near_pred = !(asdf > mp.screen_tpred);
+      // a tanh output is in [-1, 1]: anything else is an overflow of the engine's operands (fp16 range of the tensor-core
+      // engine) -- flagged per view, raised by the host when it reads view_stat back
+      if (!(asdf <= 1.0f)) atomicOr(ws.view_stat + VS_STRIDE * v + VS_NONFINITE, 1);
       // marching depth relative to the true sphere entry (renderer.py:800-804 for the pyramid variant)
       const float zstore = (mp.marching_type == DIST_MARCH_PYRAMID) ? (znew + entry) - ws.entry0[lp] : znew;
-      topk_insert(ws, P, B, lp, sdf, px, py, pz, zstore, entry + zc, 0);
+      topk_insert(ws, P, B, lp, sdf, px, py, pz, zstore, entry + zc, approx ? LVL_APPROX : 0);
       if (step + 1 < mp.march_step) {
         if (mp.marching_type == DIST_MARCH_TRIVIAL) live = true;
         else live = (znew + entry < ws.exit_[lp]) && (asdf >= mp.threshold);  // renderer.py:559-561
@@ -340,7 +388,43 @@ __global__ void k_march_update(Cam cam, dist_march_t mp, dist_workspace_t ws, in
       point_on_ray(cam, c, ray, entry + znew, p);
       nxt[idx] = lp;
       pts_nxt[(size_t)idx * 3] = p[0]; pts_nxt[(size_t)idx * 3 + 1] = p[1]; pts_nxt[(size_t)idx * 3 + 2] = p[2];
+      // a row this close to the band may be inside it after the next step: its tile skips the one-pass attempt
+      if (scr && near_pred) hint_next[idx >> 7] = 1;
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- exact re-query
+// Two-tier precision: the recorded sdf of a sample evaluated with one pass is accurate to E = screen_margin / 2 and known to
+// lie beyond the clamp.  That is enough everywhere (clamped value +-clamp_dist, zero gradient coefficient) except for the
+// ray's SMALLEST |sdf| -- min_sdf (renderer.py:382-390) and the depth estimate (:407-408) use its value.  Every one-pass
+// record that could be the true minimum (its lower bound is below the smallest upper bound) is re-evaluated at full precision.
+__global__ void k_requery_gen(dist_march_t mp, dist_workspace_t ws, int P) {
+  const int lp = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool on = lp < P && (ws.flags[lp] & 1);
+  const int B = mp.buffer_size;
+  const float E = 0.5f * mp.screen_margin;
+  float U = 3.0e38f;
+  if (on)
+    for (int b = 0; b < B; ++b)
+      U = fminf(U, fabsf(ws.top_sdf[(size_t)b * P + lp]) + ((ws.top_lvl[(size_t)b * P + lp] & LVL_APPROX) ? E : 0.f));
+  for (int b = 0; b < B; ++b) {
+    const bool cand = on && (ws.top_lvl[(size_t)b * P + lp] & LVL_APPROX) && (fabsf(ws.top_sdf[(size_t)b * P + lp]) - E <= U);
+    const int idx = warp_append(ws.rq_cnt, cand);
+    if (idx >= 0) {
+      ws.rq_idx[idx] = lp * DIST_MAX_BUFFER + b;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) ws.rq_pts[(size_t)idx * 3 + k] = ws.top_pt[((size_t)b * 3 + k) * P + lp];
+    }
+  }
+}
+
+__global__ void k_requery_apply(dist_workspace_t ws, int P) {
+  const int n = *ws.rq_cnt;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int lp = ws.rq_idx[i] / DIST_MAX_BUFFER, b = ws.rq_idx[i] % DIST_MAX_BUFFER;
+    ws.top_sdf[(size_t)b * P + lp] = ws.rq_sdf[i];
+    ws.top_lvl[(size_t)b * P + lp] = (uint8_t)((ws.top_lvl[(size_t)b * P + lp] & ~LVL_APPROX) | LVL_REQUERIED);
   }
 }
 
@@ -349,30 +433,45 @@ __global__ void k_finalize(dist_march_t mp, dist_workspace_t ws, float* Zdepth, 
   const int lp = blockIdx.x * blockDim.x + threadIdx.x;
   if (lp >= P || !(ws.flags[lp] & 1)) return;
   const int B = mp.buffer_size;
+  {   // records re-queried at full precision changed value: restore the ascending-|sdf| order (the true minimum to slot 0)
+    bool any = false;
+    for (int b = 0; b < B; ++b) any |= (ws.top_lvl[(size_t)b * P + lp] & LVL_REQUERIED) != 0;
+    if (any) {
+      for (int a = 1; a < B; ++a)
+        for (int b = a; b > 0 && fabsf(ws.top_sdf[(size_t)b * P + lp]) < fabsf(ws.top_sdf[(size_t)(b - 1) * P + lp]); --b) {
+          const size_t x = (size_t)b * P + lp, y = (size_t)(b - 1) * P + lp;
+          float t = ws.top_sdf[x]; ws.top_sdf[x] = ws.top_sdf[y]; ws.top_sdf[y] = t;
+          t = ws.top_zafter[x]; ws.top_zafter[x] = ws.top_zafter[y]; ws.top_zafter[y] = t;
+          t = ws.top_zgen[x]; ws.top_zgen[x] = ws.top_zgen[y]; ws.top_zgen[y] = t;
+          const uint8_t l = ws.top_lvl[x]; ws.top_lvl[x] = ws.top_lvl[y]; ws.top_lvl[y] = l;
+          for (int k = 0; k < 3; ++k) {
+            const size_t px = ((size_t)b * 3 + k) * P + lp, py = ((size_t)(b - 1) * 3 + k) * P + lp;
+            t = ws.top_pt[px]; ws.top_pt[px] = ws.top_pt[py]; ws.top_pt[py] = t;
+          }
+        }
+    }
+  }
   // steps this ray's view executed before all of its rays had finished (the early break of renderer.py:562 is per render)
   const int S = ws.view_stat[VS_STRIDE * (lp / Pv) + VS_STEPS];
   int nreal = ws.nreal[lp];
   const float so = ws.sdf_origin[0];
   const float zfin = ws.z[lp];
-  // renderer.py:562-567: a global early break before buffer_size steps pads the lists with copies of the last step
-  if (S < B && nreal == S && nreal > 0 && mp.marching_type != DIST_MARCH_PYRAMID) {
-    int j = 0;
-    for (int b = 0; b < nreal; ++b)
-      if (ws.top_zafter[(size_t)b * P + lp] == zfin) j = b;
-    const int pad = B - nreal;
-    for (int b = nreal - 1; b > j; --b) {  // move the tail behind the copies
-      const int d = b + pad;
-      ws.top_sdf[(size_t)d * P + lp] = ws.top_sdf[(size_t)b * P + lp];
-      ws.top_zafter[(size_t)d * P + lp] = ws.top_zafter[(size_t)b * P + lp];
-      ws.top_zgen[(size_t)d * P + lp] = ws.top_zgen[(size_t)b * P + lp];
-      for (int k = 0; k < 3; ++k) ws.top_pt[((size_t)d * 3 + k) * P + lp] = ws.top_pt[((size_t)b * 3 + k) * P + lp];
-      ws.top_lvl[(size_t)d * P + lp] = 0;
-    }
-    for (int d = j + 1; d <= j + pad; ++d) {
-      ws.top_sdf[(size_t)d * P + lp] = ws.top_sdf[(size_t)j * P + lp];
-      ws.top_zafter[(size_t)d * P + lp] = ws.top_zafter[(size_t)j * P + lp];
-      ws.top_zgen[(size_t)d * P + lp] = ws.top_zgen[(size_t)j * P + lp];
-      for (int k = 0; k < 3; ++k) ws.top_pt[((size_t)d * 3 + k) * P + lp] = ws.top_pt[((size_t)j * 3 + k) * P + lp];
+  // renderer.py:562-567: an early break of the (full-resolution) march before buffer_size steps pads its lists with
+  // copies of the last executed step; in the pyramid variant the padded fine-level lists are then concatenated with the
+  // coarse samples (renderer.py:795-801), so the copies compete with those for the top-B slots
+  if (S < B && nreal == S && nreal > 0) {
+    const float zkey = (mp.marching_type == DIST_MARCH_PYRAMID) ? (zfin + ws.entry[lp]) - ws.entry0[lp] : zfin;
+    int j = -1;
+    for (int b = 0; b < B; ++b)
+      if (ws.top_zafter[(size_t)b * P + lp] == zkey && (ws.top_lvl[(size_t)b * P + lp] & 3) == 0 &&
+          ws.top_sdf[(size_t)b * P + lp] != 1.0f) j = b;
+    if (j >= 0) {   // (evicted already: its copies would not enter either)
+      const float r_sdf = ws.top_sdf[(size_t)j * P + lp], r_za = ws.top_zafter[(size_t)j * P + lp],
+                  r_zg = ws.top_zgen[(size_t)j * P + lp];
+      const float r_p[3] = {ws.top_pt[((size_t)j * 3 + 0) * P + lp], ws.top_pt[((size_t)j * 3 + 1) * P + lp],
+                            ws.top_pt[((size_t)j * 3 + 2) * P + lp]};
+      const int r_lvl = ws.top_lvl[(size_t)j * P + lp];
+      for (int i = 0; i < B - S; ++i) topk_insert(ws, P, B, lp, r_sdf, r_p[0], r_p[1], r_p[2], r_za, r_zg, r_lvl);
     }
     nreal = B;
     ws.nreal[lp] = B;
@@ -462,7 +561,7 @@ __global__ void k_bwd_gen(dist_march_t mp, dist_workspace_t ws, const float* gZ,
 
 __global__ void k_bwd_scatter(Cam cam, dist_workspace_t ws, const int32_t* row_pix, const float* dpts,
                               const int32_t* count, float* d_cam, float* d_ray, float* d_ray_coarse, int w1, int P1v, int w2,
-                              int P2v, int P) {
+                              int P2v, int P, int cam_levels) {
   const int n = *count;
   const size_t P1 = (size_t)cam.n_views * P1v, P2 = (size_t)cam.n_views * P2v;
   // d_cam[v] accumulates per thread while consecutive rows stay in one view (rows are generated in pixel order)
@@ -472,6 +571,10 @@ __global__ void k_bwd_scatter(Cam cam, dist_workspace_t ws, const int32_t* row_p
     const int lp = row_pix[i] / DIST_MAX_BUFFER, b = row_pix[i] % DIST_MAX_BUFFER;
     const float zg = ws.top_zgen[(size_t)b * P + lp];
     if (zg != zg) continue;  // filler / off-ray sample: no camera dependence
+    const int lvl = ws.top_lvl[(size_t)b * P + lp] & 3;
+    // which samples keep their camera graph: bit 0 the full-resolution march (detached under no_grad_camera,
+    // renderer.py:536-537,543-544), bit 1 the trivial marches of the coarse pyramid levels (never detached, :481-484)
+    if (!((cam_levels >> (lvl ? 1 : 0)) & 1)) continue;
     const int v = lp / cam.Pv, lpv = lp - v * cam.Pv;
     if (v != acc_v) {
       if (acc_v >= 0)
@@ -485,7 +588,6 @@ __global__ void k_bwd_scatter(Cam cam, dist_workspace_t ws, const int32_t* row_p
     for (int k = 0; k < 3; ++k) {  // p = M^T q  ->  dL/dq = M dL/dp
       const float g = fmaf(cam.M[k * 3 + 2], d[2], fmaf(cam.M[k * 3 + 1], d[1], cam.M[k * 3] * d[0]));
       acc[k] += g;
-      const int lvl = ws.top_lvl[(size_t)b * P + lp];
       if (lvl == 0) atomicAdd(d_ray + (size_t)k * P + lp, g * zg);
       else if (d_ray_coarse) {   // sample taken on the parent (1/2) or grandparent (1/4 resolution) ray
         const int x = lpv % cam.W, y = lpv / cam.W;
@@ -518,6 +620,9 @@ int make_cam(const dist_camera_t* cam, Cam* out) {
   out->R = cam->R; out->c = cam->cam_pos;
   out->W = cam->width; out->H = cam->height; out->row0 = cam->row0; out->row_step = cam->row_step;
   out->n_rows = cam->n_rows; out->radius = cam->radius;
+  out->row_group = cam->row_group > 0 ? cam->row_group : 1;
+  DIST_REQUIRE(cam->row0 >= 0 && cam->row0 + ((cam->n_rows - 1) / out->row_group) * cam->row_step + (cam->n_rows - 1) % out->row_group < cam->height,
+               "camera: row band outside the image");
   out->n_views = n_views; out->Pv = cam->width * cam->n_rows;
   return DIST_OK;
 }
@@ -570,11 +675,28 @@ int render_depth_fwd(const dist_net_t* net, int engine, const dist_camera_t* cam
   DIST_CHECK_CUDA(cudaMemsetAsync(ws->view_stat, 0, sizeof(int32_t) * VS_STRIDE * cam.n_views, st));
   const int S_total = mp->march_step;
   const int tb = 256, gb = (P + tb - 1) / tb;
+  // two-tier precision of the march rows (tensor-core engine only)
+  const bool scr = mp->screen != 0 && engine == DIST_ENGINE_TC;
+  const int tiles = (P + 1 + 127) / 128;
+  dist_workspace_t wsv = *ws;
+  if (scr) {
+    DIST_REQUIRE(ws->tile_mode && ws->seg_approx && ws->rq_idx && ws->rq_pts && ws->rq_sdf && ws->rq_cnt,
+                 "workspace: two-tier precision buffers missing");
+    DIST_REQUIRE(mp->screen_margin > 0.f && mp->screen_tpred >= mp->clamp_dist, "two-tier precision: bad margin / prediction threshold");
+    DIST_CHECK_CUDA(cudaMemsetAsync(ws->tile_mode, 0, 3 * (size_t)tiles, st));
+    DIST_CHECK_CUDA(cudaMemsetAsync(ws->rq_cnt, 0, sizeof(int32_t), st));
+  } else {
+    wsv.tile_mode = nullptr; wsv.seg_approx = nullptr;     // the kernels key on seg_approx
+  }
+  ws = &wsv;
   Level L1, L2;
   memset(&L1, 0, sizeof(L1)); memset(&L2, 0, sizeof(L2));
   if (pyr) {
     DIST_REQUIRE(ws->pyr_f && ws->pyr_i && ws->pyr_b, "workspace: pyramid buffers missing");
-    DIST_REQUIRE(cam.row0 == 0 && cam.row_step == 1 && cam.n_rows == cam.H, "pyramid marching needs the full image (no row bands)");
+    const bool full_image = cam.row0 == 0 && cam.row_step == cam.row_group && cam.n_rows == cam.H;
+    DIST_REQUIRE(full_image || cam.row_group % 4 == 0,
+                 "pyramid marching on a row band needs bands made of 4-row groups (row_group % 4 == 0) so that the 1/2- and "
+                 "1/4-resolution levels stay band-local");
     DIST_REQUIRE(mp->coarse_steps[0] >= 1 && mp->coarse_steps[0] <= 3 && mp->coarse_steps[1] >= 1 && mp->coarse_steps[1] <= 3 &&
                      mp->coarse_steps[0] + mp->coarse_steps[1] < S_total, "pyramid marching: coarse step counts must be in [1,3]");
     carve_levels(cam, ws, &L1, &L2);
@@ -583,7 +705,11 @@ int render_depth_fwd(const dist_net_t* net, int engine, const dist_camera_t* cam
     DIST_CHECK_CUDA(cudaMemsetAsync(L1.count, 0, sizeof(int32_t) * 8, st));
     k_hit_flags<<<gb, tb, 0, st>>>(cam, *ws, P); count_launch();
     k_pyr_rays<<<(L1.P + tb - 1) / tb, tb, 0, st>>>(cam, L1, ws->flags, cam.W, cam.n_rows, nullptr); count_launch();
-    k_pyr_rays<<<(L2.P + tb - 1) / tb, tb, 0, st>>>(cam, L2, L1.hit, L1.w, L1.h, ws->view_stat); count_launch();
+    k_pyr_rays<<<(L2.P + tb - 1) / tb, tb, 0, st>>>(cam, L2, L1.hit, L1.w, L1.h, full_image ? ws->view_stat : nullptr); count_launch();
+    if (!full_image) {
+      const int w2g = ((cam.W + 1) / 2 + 1) / 2, h2g = ((cam.H + 1) / 2 + 1) / 2;
+      k_pyr_global_maxentry<<<(w2g * h2g * cam.n_views + tb - 1) / tb, tb, 0, st>>>(cam, w2g, h2g, ws->view_stat); count_launch();
+    }
     for (int lv = 2; lv >= 1; --lv) {
       Level& L = (lv == 2) ? L2 : L1;
       k_pyr_start<<<(L.P + tb - 1) / tb, tb, 0, st>>>(cam, L, L2, lv == 1 ? 1 : 0, ws->view_stat, ws->pts); count_launch();
@@ -591,6 +717,7 @@ int render_depth_fwd(const dist_net_t* net, int engine, const dist_camera_t* cam
       for (int s = 0; s < ns; ++s) {
         MlpArgs a{};
         a.points = ws->pts; a.n_host = L.P; a.n_dev = L.count; a.clamp_dist = 0.f; a.sdf = ws->sdf; a.rows_evaluated = rows_eval;
+        a.tile_counters = ws->tile_counters;
         rc = mlp_launch(net, nd, engine, 0, a, st);
         if (rc) return rc;
         k_pyr_step<<<min((L.P + tb - 1) / tb, 4 * num_sms()), tb, 0, st>>>(cam, *mp, L, s, ws->pts, ws->sdf); count_launch();
@@ -599,7 +726,8 @@ int render_depth_fwd(const dist_net_t* net, int engine, const dist_camera_t* cam
   }
   const int S = mp->march_step;
   DIST_CHECK_CUDA(cudaMemsetAsync(ws->counts, 0, sizeof(int32_t) * (S_total + 2), st));
-  k_setup<<<gb, tb, 0, st>>>(cam, *mp, *ws, Zdepth, mask, min_sdf, P, L1, L2); count_launch();
+  k_setup<<<(cam.n_views * setup_threads_per_view(cam.W, cam.n_rows) + tb - 1) / tb, tb, 0, st>>>(cam, *mp, *ws, Zdepth, mask, min_sdf, P,
+                                                                                                L1, L2); count_launch();
   k_append_origin<<<1, 1, 0, st>>>(*ws, S + 1); count_launch();
   DIST_CHECK_CUDA(cudaGetLastError());
   const int gu = min(gb, 4 * num_sms());
@@ -608,9 +736,24 @@ int render_depth_fwd(const dist_net_t* net, int engine, const dist_camera_t* cam
     a.points = ws->pts + (size_t)(s & 1) * (size_t)(P + 1) * 3; a.n_host = P + (s == 0 ? 1 : 0);
     a.n_dev = ws->counts + (s == 0 ? S + 1 : s);
     a.clamp_dist = 0.f; a.sdf = ws->sdf; a.rows_evaluated = rows_eval;
+    a.tile_counters = ws->tile_counters;
+    if (scr) {
+      a.tile_mode = ws->tile_mode + (size_t)(s % 3) * tiles; a.screen_thresh = mp->clamp_dist + mp->screen_margin;
+      a.exact_last = (s == 0) ? 1 : 0;      // the origin query of step 0 (filler samples, renderer.py:539-540) is exact
+      a.seg_approx = ws->seg_approx;
+    }
     rc = mlp_launch(net, nd, engine, 0, a, st);
     if (rc) return rc;
-    k_march_update<<<gu, tb, 0, st>>>(cam, *mp, *ws, s, P); count_launch();
+    k_march_update<<<gu, tb, 0, st>>>(cam, *mp, *ws, s, P, tiles); count_launch();
+  }
+  if (scr) {
+    k_requery_gen<<<gb, tb, 0, st>>>(*mp, *ws, P); count_launch();
+    MlpArgs a{};
+    a.points = ws->rq_pts; a.n_host = (int64_t)P * mp->buffer_size; a.n_dev = ws->rq_cnt; a.clamp_dist = 0.f; a.sdf = ws->rq_sdf;
+    a.tile_counters = ws->tile_counters;
+    rc = mlp_launch(net, nd, engine, 0, a, st);
+    if (rc) return rc;
+    k_requery_apply<<<gu, tb, 0, st>>>(*ws, P); count_launch();
   }
   k_finalize<<<gb, tb, 0, st>>>(*mp, *ws, Zdepth, mask, min_sdf, P, cam.Pv); count_launch();
   DIST_CHECK_CUDA(cudaGetLastError());
@@ -664,7 +807,8 @@ int render_depth_bwd(const dist_net_t* net, int engine, const dist_camera_t* cam
   if (d_cam && d_ray) {
     const int w1 = (cam.W + 1) / 2, h1 = (cam.n_rows + 1) / 2, w2 = (w1 + 1) / 2, h2 = (h1 + 1) / 2;
     k_bwd_scatter<<<min((int)(((int64_t)P * mp->buffer_size + tb - 1) / tb), 4 * num_sms()), tb, 0, st>>>(
-        cam, *ws, s_row_pix, s_dpts, s_count, d_cam, d_ray, d_ray_coarse, w1, w1 * h1, w2, w2 * h2, P); count_launch();
+        cam, *ws, s_row_pix, s_dpts, s_count, d_cam, d_ray, d_ray_coarse, w1, w1 * h1, w2, w2 * h2, P,
+        mp->cam_grad_levels ? mp->cam_grad_levels : 3); count_launch();
   }
   DIST_CHECK_CUDA(cudaGetLastError());
   return DIST_OK;

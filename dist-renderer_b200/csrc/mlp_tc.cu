@@ -41,7 +41,9 @@ constexpr int OFF_AHI = 0, OFF_ALO = 65536, OFF_W = 131072;
 constexpr int OFF_BAR = OFF_W + NST * STAGE_BYTES;   // 229376
 constexpr int OFF_PART = OFF_BAR + 512;              // per-row partial sums [64][8] (8 threads share a row)
 constexpr int OFF_ROWD = OFF_PART + 2048;            // per-row scalar [64]
-constexpr int SMEM_BYTES = OFF_ROWD + 256;           // 232192
+constexpr int OFF_FAIL = OFF_ROWD + 256;             // two-tier precision: [near flag u32][pad][fail bitmap, FAIL_WORDS u32]
+constexpr int FAIL_WORDS = 32;                       // 1024 tiles per cluster and launch (7 M rows on 74 clusters)
+constexpr int SMEM_BYTES = OFF_FAIL + 16 + 4 * FAIL_WORDS;   // 232336 (limit 232448)
 constexpr int NTHREADS = 640;                        // 4 service warps + 16 epilogue warps
 constexpr int MAX_PROG = 2 * 10;                     // forward + transposed chain, at most 10 tensor-core layers each
 
@@ -79,6 +81,12 @@ struct TcIO {
   float* sdf; float* grad; const float* coef; const uint8_t* use_clamp; float* acc0; float* accl;
   int64_t* rows_evaluated;
   long long* dbg_out;   // DIST_TC_DEBUG bit2: [cycles, ns] of CTA 0
+  // two-tier precision (MODE 0 only; see the kernel comment).  tile_mode == nullptr: every tile at full precision.
+  const uint8_t* tile_mode;     // [tiles] 0: try ONE fp16 pass first ("screen"), != 0: three split-precision passes directly
+  float screen_thresh;          // a screened half-tile passes when all its rows have |sdf| > screen_thresh
+  int exact_last;               // the tile that holds the last row (the march's origin query) is never screened
+  uint8_t* seg_approx;          // [ceil(n/64)] out: 1 = the sdf of this 64-row half-tile are one-pass values
+  unsigned long long* tile_counters;   // optional [2]: += tiles evaluated with one pass / with three passes
 };
 
 // --------------------------------------------------------------------------------------------- PTX helpers
@@ -110,6 +118,13 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_local, uint32_t
   uint32_t remote;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(bar_local), "r"(target_rank));
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+// 32-bit load from the same shared-memory offset of CTA `rank` of this cluster (distributed shared memory)
+__device__ __forceinline__ uint32_t ld_dsmem_u32(uint32_t local_addr, uint32_t rank) {
+  uint32_t remote, v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_addr), "r"(rank));
+  asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(remote) : "memory");
+  return v;
 }
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
   uint64_t d = 0;
@@ -155,17 +170,21 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 }
 
 // Writes 8 consecutive features (one K-group panel row) of this thread's row: x[] already multiplied by sA.
-__device__ __forceinline__ void store_group(uint8_t* smem, int feat0, int row, const float* x) {
+// with_lo = false (one-pass tiles): only the hi half is read by the MMAs, the lo half is left stale
+__device__ __forceinline__ void store_group(uint8_t* smem, int feat0, int row, const float* x, bool with_lo = true) {
   __half2 h[4], l[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    h[i] = __floats2half2_rn(x[2 * i], x[2 * i + 1]);
-    const float2 hf = __half22float2(h[i]);
-    l[i] = __floats2half2_rn(x[2 * i] - hf.x, x[2 * i + 1] - hf.y);
-  }
+  for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(x[2 * i], x[2 * i + 1]);
   const int off = (feat0 >> 3) * 1024 + row * 16;
   *reinterpret_cast<uint4*>(smem + OFF_AHI + off) = *reinterpret_cast<uint4*>(h);
-  *reinterpret_cast<uint4*>(smem + OFF_ALO + off) = *reinterpret_cast<uint4*>(l);
+  if (with_lo) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 hf = __half22float2(h[i]);
+      l[i] = __floats2half2_rn(x[2 * i] - hf.x, x[2 * i + 1] - hf.y);
+    }
+    *reinterpret_cast<uint4*>(smem + OFF_ALO + off) = *reinterpret_cast<uint4*>(l);
+  }
 }
 
 // --------------------------------------------------------------------------------------------- kernel
@@ -173,7 +192,7 @@ __device__ __forceinline__ void store_group(uint8_t* smem, int feat0, int row, c
 // upstream coefficients: d/dxyz per row and the row-summed pre-activation gradients of layer 0 / the latent_in layer.
 template <int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
-mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P, const TcIO io) {
+mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_hi, const TcParams P, const TcIO io) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int64_t n = io.n_dev ? (int64_t)*io.n_dev : io.n_host;
   if (n <= 0) return;
@@ -197,12 +216,42 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P, const 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 8 * (2 * NST + 37));
   const int n_prog = P.n_prog;
 
+  // ---- two-tier precision (MODE 0 with io.tile_mode): a tile whose mode byte is 0 is first evaluated with ONE fp16 pass
+  // (A_hi W_hi; only the hi halves of the weight stages are fetched).  If all 64 rows of a CTA come out with
+  // |sdf| > screen_thresh (safely beyond the march's clamp, so the step they cause does not depend on their last bits)
+  // the half-tile is done and flagged in io.seg_approx; if either CTA of the pair sees a nearer row the tile is recorded
+  // in that CTA's fail bitmap and re-evaluated at full precision in a second pass over this cluster's tiles ("phase 1")
+  // after a cluster barrier -- no other communication between roles or CTAs is needed, every role walks the same lists.
+  const int cnt = (cluster_id < n_tiles) ? (int)((n_tiles - cluster_id + n_clusters - 1) / n_clusters) : 0;  // tiles of this cluster
+  const bool screening = (MODE == 0) && io.tile_mode != nullptr && cnt <= 32 * FAIL_WORDS;
+  volatile uint32_t* near_flag = reinterpret_cast<volatile uint32_t*>(smem + OFF_FAIL);
+  volatile uint32_t* fail_words = reinterpret_cast<volatile uint32_t*>(smem + OFF_FAIL + 16);
+  const uint32_t fail_addr = sbase + OFF_FAIL + 16;
+  auto tile_of = [&](int i) -> int64_t { return cluster_id + (int64_t)i * n_clusters; };
+  auto tile_exact = [&](int64_t t) -> bool {
+    return !screening || io.tile_mode[t] != 0 || (io.exact_last && t == n_tiles - 1);
+  };
+  // next tile index of this cluster after i (i = -1: the first), -1 when exhausted.  phase 0: all tiles; phase 1: tiles
+  // whose fail bit is set in this CTA's or the peer's bitmap (read through distributed shared memory)
+  auto next_tile = [&](int phase, int i) -> int {
+    if (phase == 0) return (i + 1 < cnt) ? i + 1 : -1;
+    int j = i + 1;
+    while (j < cnt) {
+      const uint32_t w = (fail_words[j >> 5] | ld_dsmem_u32(fail_addr + 4 * (j >> 5), rank ^ 1u)) >> (j & 31);
+      if (w) { j += __ffs(w) - 1; return (j < cnt) ? j : -1; }
+      j = (j | 31) + 1;
+    }
+    return -1;
+  };
+
   if (tid == 0) {
     for (int s = 0; s < NST; ++s) { mbar_init(W_FULL(s), 1); mbar_init(W_EMPTY(s), 1); }
     for (int c = 0; c < 16; ++c) mbar_init(A_FULL(c), 4);  // 2 warps x 2 CTAs produce each 32-feature block
     for (int c = 0; c < 16; ++c) mbar_init(A_FREE(c), 1);
     for (int b = 0; b < 2; ++b) { mbar_init(D_FULL(b, 0), 1); mbar_init(D_FULL(b, 1), 1); }
     mbar_init(FIN, 32);                                     // 16 epilogue warps x 2 CTAs
+    *near_flag = 0u;
+    for (int w = 0; w < FAIL_WORDS; ++w) fail_words[w] = 0u;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -222,24 +271,33 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P, const 
     {
       uint32_t p_slot = 0, p_phase = 0;
       const uint32_t bar_leader_mask = 0xFEFFFFFFu;
-      for (int64_t t = cluster_id; t < n_tiles; t += n_clusters) {
-        for (int m = 0; m < n_prog; ++m) {
-          const int nstage = P.L[m].kc32 * P.L[m].nh, sb = P.L[m].stage_base;
-          for (int s = 0; s < nstage; ++s) {
-            const uint32_t slot = p_slot, ph = p_phase;
-            if (++p_slot == NST) { p_slot = 0; p_phase ^= 1; }
-            mbar_wait(W_EMPTY(slot), ph ^ 1);
-            if (elect_one()) {
-              if (rank == 0) mbar_expect_tx(W_FULL(slot), 2 * STAGE_BYTES);
-              const int row = ((sb + s) * 2 + (int)rank) * (STAGE_BYTES / 128);
-              asm volatile(
-                  "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
-                      "r"(sbase + OFF_W + slot * STAGE_BYTES),
-                  "l"(&tmap), "r"(W_FULL(slot) & bar_leader_mask), "r"(0), "r"(row)
-                  : "memory");
+      for (int phase = 0; phase < 2; ++phase) {
+        for (int i = next_tile(phase, -1); i >= 0; i = next_tile(phase, i)) {
+          const bool exact = (phase == 1) || tile_exact(tile_of(i));
+          const CUtensorMap* tm = exact ? &tmap : &tmap_hi;          // one-pass tiles fetch [hi 8 KB] of each stage only
+          const uint32_t bytes = exact ? 2 * STAGE_BYTES : STAGE_BYTES;
+          for (int m = 0; m < n_prog; ++m) {
+            const int nstage = P.L[m].kc32 * P.L[m].nh, sb = P.L[m].stage_base;
+            for (int s = 0; s < nstage; ++s) {
+              const uint32_t slot = p_slot, ph = p_phase;
+              if (++p_slot == NST) { p_slot = 0; p_phase ^= 1; }
+              mbar_wait(W_EMPTY(slot), ph ^ 1);
+              if (elect_one()) {
+                if (rank == 0) mbar_expect_tx(W_FULL(slot), bytes);
+                const int row = ((sb + s) * 2 + (int)rank) * (STAGE_BYTES / 128);
+                asm volatile(
+                    "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
+                        "r"(sbase + OFF_W + slot * STAGE_BYTES),
+                    "l"(tm), "r"(W_FULL(slot) & bar_leader_mask), "r"(0), "r"(row)
+                    : "memory");
+              }
+              __syncwarp();
             }
-            __syncwarp();
           }
+        }
+        if (phase == 0) {
+          if (!screening) break;
+          cluster_sync_all();     // every thread of both CTAs: the fail bitmaps are complete
         }
       }
     }
@@ -253,7 +311,11 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P, const 
       const uint64_t b_0 = make_desc(sbase + OFF_W, 2048, 128);
       uint32_t G = 0, a_phase = 0, fin_phase = 0, w_slot = 0, w_phase = 0;
       uint32_t d_first = 1;
-      for (int64_t t = cluster_id; t < n_tiles; t += n_clusters) {
+      for (int phase = 0; phase < 2; ++phase) {
+      for (int i = next_tile(phase, -1); i >= 0; i = next_tile(phase, i)) {
+        const int64_t t = tile_of(i);
+        const bool exact = (phase == 1) || tile_exact(t);   // one-pass tiles issue A_hi W_hi only
+        (void)t;
         for (int m = 0; m < n_prog; ++m, ++G) {
           const int kc32 = P.L[m].kc32, nh = P.L[m].nh;
           const uint32_t buf = G & 1;
@@ -293,8 +355,10 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P, const 
                     const uint64_t a_off = (uint64_t)(((kc + u) * 4 + ks * 2) * 64);
                     const uint64_t b_off = (uint64_t)(slot * (STAGE_BYTES / 16) + ks * 256);
                     mma_f16_2cta(d_addr, a_hi0 + a_off, b_0 + b_off, idesc, ((kc + u) | ks) ? 1u : 0u);
-                    mma_f16_2cta(d_addr, a_lo0 + a_off, b_0 + b_off, idesc, 1u);
-                    mma_f16_2cta(d_addr, a_hi0 + a_off, b_0 + b_off + 512, idesc, 1u);
+                    if (exact) {
+                      mma_f16_2cta(d_addr, a_lo0 + a_off, b_0 + b_off, idesc, 1u);
+                      mma_f16_2cta(d_addr, a_hi0 + a_off, b_0 + b_off + 512, idesc, 1u);
+                    }
                   }
                   commit_mc(W_EMPTY(slot));
                   if (last_pass) commit_mc(A_FREE(kc + u));
@@ -311,8 +375,17 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P, const 
         }
         d_first = 0;
       }
+        if (phase == 0) {
+          if (!screening) break;
+          cluster_sync_all();
+        }
+      }
+    } else if (screening) {
+      cluster_sync_all();     // the non-leader CTA's MMA warp only takes part in the phase barrier
     }
-  } else if (warp >= 4) {
+  } else if (warp < 4) {
+    if (screening) cluster_sync_all();   // TMEM-allocator warp and the spare warp: phase barrier only
+  } else {
     // =============================================================== epilogue warps (16 warps, 32 rows x 32 columns each)
     const int ew = warp - 4;
     const int qq = warp & 3;             // TMEM lane quarter accessible to this warp
@@ -389,9 +462,14 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P, const 
       return ((pr[0] + pr[1]) + (pr[2] + pr[3])) + ((pr[4] + pr[5]) + (pr[6] + pr[7]));
     };
 
-    int64_t t = cluster_id;
-    if (t < n_tiles) { load_point(t); layer0(); }
-    for (; t < n_tiles; t += n_clusters) {
+    unsigned int n_tiles_1pass = 0, n_tiles_3pass = 0;   // tile programs this cluster evaluated (rank 0, warp 4, lane 0)
+    for (int phase = 0; phase < 2; ++phase) {
+    int i = next_tile(phase, -1);
+    if (i >= 0) { load_point(tile_of(i)); layer0(); }
+    while (i >= 0) {
+      const int64_t t = tile_of(i);
+      const int inext = next_tile(phase, i);
+      const bool exact = (phase == 1) || tile_exact(t);
       const int64_t gr = t * 128 + rank * 64 + row;
       float dot = 0.f, rowscale = 0.f, dx = 0.f, dy = 0.f, dz = 0.f;
       uint32_t mk0s[2] = {0u, 0u};
@@ -416,7 +494,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P, const 
         };
         // the next tile's points are fetched before the wait so that their latency hides behind the last MMAs
         // (px/py/pz of this tile are no longer needed: xyz is only appended in earlier forward layers)
-        if (prog_last && t + n_clusters < n_tiles) load_point(t + n_clusters);
+        if (prog_last && inext >= 0) load_point(tile_of(inext));
         if (prog_last) for (int h = 0; h < Lnh; ++h) wait_half(h);   // all MMAs of the tile done before A is recycled
 #ifdef DIST_TC_TIMELINE
         const bool dbg_rec = io.dbg_out && cluster_id == 0 && rank == 0 && warp == 4 && lane == 0 && t == cluster_id + n_clusters;
@@ -426,7 +504,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P, const 
         if (prog_last) {
           // all MMAs of this tile are complete: A is free -> start the next tile's layer 0 before draining D
           if (MODE != 0) { mk0s[0] = mk[0][0]; mk0s[1] = mk[0][1]; }
-          if (t + n_clusters < n_tiles) layer0();
+          if (inext >= 0) layer0();
         }
         const int kblocks_next = prog_last ? 0 : P.L[m + 1].kc32;
         // net layer whose ReLU mask gates the values produced here (transposed chain): l-1 with l = 2 n_mma - m
@@ -492,7 +570,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P, const 
             } else if (need_store) {
               wait_free(kb);
 #pragma unroll
-              for (int g = 0; g < 4; ++g) store_group(smem, fb + 8 * g, row, &v[8 * g]);
+              for (int g = 0; g < 4; ++g) store_group(smem, fb + 8 * g, row, &v[8 * g], exact);
               signal_block(kb);
             }
           } else {
@@ -564,6 +642,8 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P, const 
             float oc = o;
             if (io.clamp_dist > 0.f) oc = fminf(fmaxf(o, -io.clamp_dist), io.clamp_dist);
             if (gr < n && io.sdf) io.sdf[gr] = oc;
+            // one-pass tile: a row that may be inside the clamp band (or is not a number) fails the half-tile
+            if (MODE == 0 && !exact && gr < n && !(fabsf(o) > io.screen_thresh)) *near_flag = 1u;
             if (MODE != 0) {
               float d = 1.f - o * o;
               if (P.use_tanh) d *= (1.f - t1 * t1);
@@ -577,6 +657,15 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P, const 
             }
           }
           epi_bar_sync();
+          if (MODE == 0 && ew == 0 && lane == 0) {
+            bool approx = false;
+            if (!exact) {
+              if (*near_flag) { fail_words[i >> 5] |= 1u << (i & 31); *near_flag = 0u; }   // redo in phase 1
+              else approx = true;
+            }
+            if (io.seg_approx && (t * 2 + rank) * 64 < n) io.seg_approx[t * 2 + rank] = approx ? 1 : 0;
+            if (exact) ++n_tiles_3pass; else ++n_tiles_1pass;
+          }
           if (MODE != 0) {
             rowscale = rowd[row];
             // seed of the transposed chain (unit): delta[f] = w_last[f] * relu'(f), as A of the first transposed layer
@@ -622,6 +711,17 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P, const 
           }
         }
       }
+      i = inext;
+    }
+      if (phase == 0) {
+        if (!screening) break;
+        cluster_sync_all();       // both CTAs' fail bitmaps are final; phase 1 re-evaluates those tiles at full precision
+      }
+    }
+    if (io.tile_counters && rank == 0 && ew == 0 && lane == 0) {
+      if (MODE != 0) n_tiles_3pass = 2u * (unsigned)cnt;      // forward + transposed chain
+      if (n_tiles_1pass) atomicAdd(io.tile_counters, (unsigned long long)n_tiles_1pass);
+      if (n_tiles_3pass) atomicAdd(io.tile_counters + 1, (unsigned long long)n_tiles_3pass);
     }
     if (MODE == 2) {
       // flush the per-lane running column sums: lane j of this warp holds column 32*kb + j of its blocks
@@ -715,6 +815,10 @@ int mlp_tc_launch(const dist_net_t* net, const NetDev& nd, int mode, const MlpAr
   io.points = a.points; io.n_host = a.n_host; io.n_dev = a.n_dev; io.clamp_dist = a.clamp_dist;
   io.sdf = a.sdf; io.grad = a.grad; io.coef = a.coef; io.use_clamp = a.use_clamp; io.acc0 = a.acc0; io.accl = a.accl;
   io.rows_evaluated = a.rows_evaluated;
+  io.tile_mode = (mode == 0) ? a.tile_mode : nullptr;
+  io.screen_thresh = a.screen_thresh; io.exact_last = a.exact_last; io.seg_approx = a.seg_approx;
+  io.tile_counters = a.tile_counters;
+  DIST_REQUIRE(io.tile_mode == nullptr || io.seg_approx != nullptr, "tensor-core engine: two-tier precision needs seg_approx");
   io.dbg_out = nullptr;
   static long long* dbg_buf = nullptr;
   if (P.dbg & 4) { if (!dbg_buf) { cudaMalloc(&dbg_buf, 2048); cudaMemset(dbg_buf, 0, 2048); } io.dbg_out = dbg_buf; }
@@ -730,6 +834,13 @@ int mlp_tc_launch(const dist_net_t* net, const NetDev& nd, int mode, const MlpAr
                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)cr); return DIST_E_CUDA; }
+  // same blob, boxes of the first 8 KB ([hi]) of a stage only: what a one-pass tile fetches
+  CUtensorMap tmap_hi;
+  const cuuint32_t box_hi[2] = {64, STAGE_BYTES / 256};
+  cr = encode(&tmap_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(net->tc_blob), gdim, gstr, box_hi, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (hi box) failed (%d)", (int)cr); return DIST_E_CUDA; }
 
   static bool attr_done_dev[64] = {false};
   int cur_dev = 0;
@@ -745,9 +856,9 @@ int mlp_tc_launch(const dist_net_t* net, const NetDev& nd, int mode, const MlpAr
   int clusters = num_sms() / 2;
   if (tiles < clusters) clusters = (int)tiles;
   if (clusters < 1) clusters = 1;
-  if (mode == 0) { mlp_tc_kernel<0><<<clusters * 2, NTHREADS, SMEM_BYTES, stream>>>(tmap, P, io); }
-  else if (mode == 1) { mlp_tc_kernel<1><<<clusters * 2, NTHREADS, SMEM_BYTES, stream>>>(tmap, P, io); }
-  else { mlp_tc_kernel<2><<<clusters * 2, NTHREADS, SMEM_BYTES, stream>>>(tmap, P, io); }
+  if (mode == 0) { mlp_tc_kernel<0><<<clusters * 2, NTHREADS, SMEM_BYTES, stream>>>(tmap, tmap_hi, P, io); }
+  else if (mode == 1) { mlp_tc_kernel<1><<<clusters * 2, NTHREADS, SMEM_BYTES, stream>>>(tmap, tmap_hi, P, io); }
+  else { mlp_tc_kernel<2><<<clusters * 2, NTHREADS, SMEM_BYTES, stream>>>(tmap, tmap_hi, P, io); }
   count_launch();
   DIST_CHECK_CUDA(cudaGetLastError());
   if (P.dbg & 4) {

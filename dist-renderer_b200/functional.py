@@ -21,8 +21,14 @@ def resolve_engine(plan, engine):
     return _ENGINES[engine]
 
 
-def _stream():
-    return torch.cuda.current_stream().cuda_stream
+def _stream(device):
+    """The caller's current stream on `device` (the tensors' device, not whatever device is current)."""
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _check_device(plan, points):
+    if points.device != plan.device:
+        raise ValueError("points live on %s but the decoder on %s" % (points.device, plan.device))
 
 
 def _check_points(points):
@@ -36,14 +42,16 @@ class _DecodeFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, latent, points, plan, clamp_dist, engine):
         lib = _abi.lib()
-        st = _stream()
-        net, engine, _keep = plan.net_for(latent, engine, st)
-        pts = points.detach().float().contiguous()
-        n = pts.shape[0]
-        sdf = torch.empty(n, 1, device=pts.device, dtype=torch.float32)
-        cd = float(clamp_dist) if clamp_dist is not None else 0.0
-        if n > 0:
-            _abi.check(lib.dist_decoder_forward(net, engine, _abi.ptr(pts), n, None, cd, _abi.ptr(sdf), st))
+        _check_device(plan, points)
+        with torch.cuda.device(plan.device):
+            st = _stream(plan.device)
+            net, engine, _keep = plan.net_for(latent, engine, st)
+            pts = points.detach().float().contiguous()
+            n = pts.shape[0]
+            sdf = torch.empty(n, 1, device=pts.device, dtype=torch.float32)
+            cd = float(clamp_dist) if clamp_dist is not None else 0.0
+            if n > 0:
+                _abi.check(lib.dist_decoder_forward(net, engine, _abi.ptr(pts), n, None, cd, _abi.ptr(sdf), st))
         ctx.plan, ctx.cd, ctx.engine = plan, cd, engine
         ctx.save_for_backward(pts, latent if latent is not None else torch.empty(0, device=pts.device))
         ctx.has_latent = latent is not None
@@ -52,16 +60,18 @@ class _DecodeFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         pts, latent = ctx.saved_tensors
-        plan, lib, st = ctx.plan, _abi.lib(), _stream()
-        net, eng_b, _keep = plan.net_for(latent if ctx.has_latent else None, ctx.engine, st)
-        n = pts.shape[0]
-        coef = g.detach().reshape(-1).float().contiguous()
-        dpts = torch.zeros(n, 3, device=pts.device)
-        acc0 = torch.zeros(plan.bias[0].numel(), device=pts.device)
-        accl = torch.zeros(plan.bias[plan.latent_in].numel(), device=pts.device) if plan.latent_in >= 0 else None
-        if n > 0:
-            _abi.check(lib.dist_decoder_backward(net, eng_b, _abi.ptr(pts), _abi.ptr(coef), None, n, None, ctx.cd,
-                                                 _abi.ptr(dpts), _abi.ptr(acc0), _abi.ptr(accl), st))
+        plan, lib = ctx.plan, _abi.lib()
+        with torch.cuda.device(plan.device):
+            st = _stream(plan.device)
+            net, eng_b, _keep = plan.net_for(latent if ctx.has_latent else None, ctx.engine, st)
+            n = pts.shape[0]
+            coef = g.detach().reshape(-1).float().contiguous()
+            dpts = torch.zeros(n, 3, device=pts.device)
+            acc0 = torch.zeros(plan.bias[0].numel(), device=pts.device)
+            accl = torch.zeros(plan.bias[plan.latent_in].numel(), device=pts.device) if plan.latent_in >= 0 else None
+            if n > 0:
+                _abi.check(lib.dist_decoder_backward(net, eng_b, _abi.ptr(pts), _abi.ptr(coef), None, n, None, ctx.cd,
+                                                     _abi.ptr(dpts), _abi.ptr(acc0), _abi.ptr(accl), st))
         g_lat = plan.latent_grad(acc0, accl).reshape(latent.shape) if (ctx.has_latent and ctx.needs_input_grad[0]) \
             else None
         return g_lat, (dpts if ctx.needs_input_grad[1] else None), None, None, None
@@ -95,14 +105,16 @@ def decode_sdf_gradient(decoder, latent_vector, points, clamp_dist=0.1, MAX_POIN
     lib = _abi.lib()
     plan = plan_for(decoder)
     eng = resolve_engine(plan, engine or DEFAULT_ENGINE)
-    st = _stream()
-    net, eng, _keep = plan.net_for(latent_vector, eng, st)
-    pts = points.detach().float().contiguous()
-    n = pts.shape[0]
-    grad = torch.empty(n, 3, device=pts.device)
-    cd = float(clamp_dist) if clamp_dist is not None else 0.0
-    if n > 0:
-        _abi.check(lib.dist_decoder_input_grad(net, eng, _abi.ptr(pts), n, None, cd, _abi.ptr(grad), None, st))
+    _check_device(plan, points)
+    with torch.cuda.device(plan.device):
+        st = _stream(plan.device)
+        net, eng, _keep = plan.net_for(latent_vector, eng, st)
+        pts = points.detach().float().contiguous()
+        n = pts.shape[0]
+        grad = torch.empty(n, 3, device=pts.device)
+        cd = float(clamp_dist) if clamp_dist is not None else 0.0
+        if n > 0:
+            _abi.check(lib.dist_decoder_input_grad(net, eng, _abi.ptr(pts), n, None, cd, _abi.ptr(grad), None, st))
     return grad
 
 

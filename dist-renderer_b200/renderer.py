@@ -27,8 +27,9 @@ _MARCH = {"trivial": _abi.MARCH_TRIVIAL, "trivial_non_parallel": _abi.MARCH_TRIV
           "recursive": _abi.MARCH_RECURSIVE, "pyramid_recursive": _abi.MARCH_PYRAMID}
 
 
-def _stream():
-    return torch.cuda.current_stream().cuda_stream
+def _stream(device=None):
+    """The caller's current stream ON THE RENDERER'S DEVICE (not on whatever device happens to be current)."""
+    return torch.cuda.current_stream(device).cuda_stream
 
 
 class _RenderDepthFn(torch.autograd.Function):
@@ -36,7 +37,12 @@ class _RenderDepthFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, latent, R, T, ren, opts):
-        lib, st = _abi.lib(), _stream()
+        with torch.cuda.device(ren.device):     # the library launches on the current device: make it the renderer's
+            return _RenderDepthFn._forward(ctx, latent, R, T, ren, opts)
+
+    @staticmethod
+    def _forward(ctx, latent, R, T, ren, opts):
+        lib, st = _abi.lib(), _stream(ren.device)
         plan = ren.plan
         plan.refresh()
         dev = ren.device
@@ -53,6 +59,12 @@ class _RenderDepthFn(torch.autograd.Function):
         pyr = opts["kind"] == "pyramid_recursive"
         if pyr:
             mp.coarse_steps[0], mp.coarse_steps[1] = ren._coarse_steps()
+        mp.cam_grad_levels = opts["cam_levels"]
+        # two-tier precision of the march rows (tc.py): only on the tensor-core engine, only when the one-pass values of
+        # this decoder were measured to be accurate to half the margin
+        screen = plan.tc.get("screen") if (engine == _abi.ENGINE_TC and plan.tc is not None and ren.screen) else None
+        if screen:
+            mp.screen, mp.screen_margin, mp.screen_tpred = 1, screen["margin"], ren.screen_tpred
         f32 = dict(device=dev, dtype=torch.float32)
         saved = {
             "flags": torch.empty(P, device=dev, dtype=torch.uint8), "nreal": torch.empty(P, device=dev, dtype=torch.int32),
@@ -66,6 +78,7 @@ class _RenderDepthFn(torch.autograd.Function):
         for name in _abi.WS_FIELDS:
             t = saved.get(name, scr.get(name))
             setattr(ws, name, t.data_ptr() if t is not None else None)
+        ws.tile_counters = ren.tile_counters.data_ptr()
         Zdepth = torch.empty(P, **f32)
         mask = torch.empty(P, device=dev, dtype=torch.uint8)
         min_sdf = torch.empty(P, **f32)
@@ -83,8 +96,13 @@ class _RenderDepthFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gZ, _gmask, gM, _ghit):
+        with torch.cuda.device(ctx.ren.device):
+            return _RenderDepthFn._backward(ctx, gZ, gM)
+
+    @staticmethod
+    def _backward(ctx, gZ, gM):
         latent, Rd, Td = ctx.saved_tensors
-        ren, opts, lib, st = ctx.ren, ctx.opts, _abi.lib(), _stream()
+        ren, opts, lib, st = ctx.ren, ctx.opts, _abi.lib(), _stream(ctx.ren.device)
         plan, dev, P, B = ren.plan, ren.device, ren.P, ren.buffer_size
         net, eng_b, _keep = plan.net_for(latent, ctx.engine, st)
         cam_pos = ren.get_camera_location(Rd, Td).contiguous()
@@ -98,7 +116,7 @@ class _RenderDepthFn(torch.autograd.Function):
         pyr = opts["kind"] == "pyramid_recursive"
         gZ = gZ.contiguous().float() if (gZ is not None and opts["want_depth_grad"]) else None
         gM = gM.contiguous().float() if (gM is not None and opts["want_mask_grad"]) else None
-        want_cam = opts["want_camera_grad"] and (ctx.needs_input_grad[1] or ctx.needs_input_grad[2])
+        want_cam = opts["cam_levels"] != 0 and (ctx.needs_input_grad[1] or ctx.needs_input_grad[2])
         f32 = dict(device=dev, dtype=torch.float32)
         acc0 = torch.zeros(plan.bias[0].numel(), **f32)
         accl = torch.zeros(plan.bias[plan.latent_in].numel(), **f32) if plan.latent_in >= 0 else None
@@ -138,7 +156,7 @@ class SDFRenderer(object):
     def __init__(self, decoder, intrinsic, img_hw=None, transform_matrix=None, march_step=50, buffer_size=5,
                  ray_marching_ratio=1.5, use_depth2normal=False, max_sample_dist=0.2, radius=1.0, threshold=5e-5,
                  scale_list=[4, 2, 1], march_step_list=[3, 3, -1], use_gpu=True, is_eval=True, engine=None,
-                 rows=None):
+                 rows=None, screen=None, screen_tpred=0.28):
         # renderer.py:13-59
         self.decoder = decoder
         if use_gpu and torch.cuda.device_count() == 0:
@@ -167,10 +185,13 @@ class SDFRenderer(object):
             img_hw = (int(self.intrinsic[1, 2] * 2), int(self.intrinsic[0, 2] * 2))
         self.img_hw = (int(img_hw[0]), int(img_hw[1]))
         h, w = self.img_hw
-        self.rows = (0, 1, h) if rows is None else tuple(int(v) for v in rows)
-        row0, step, n_rows = self.rows
-        if not (0 <= row0 and step >= 1 and n_rows >= 1 and row0 + (n_rows - 1) * step < h):
-            raise ValueError("rows=(row0,row_step,n_rows) outside the image")
+        # rows = (row0, row_step, n_rows[, row_group]): local row l is image row row0 + (l // g) * row_step + l % g
+        self.rows = (0, 1, h, 1) if rows is None else (tuple(int(v) for v in rows) + (1,))[:4]
+        row0, step, n_rows, grp = self.rows
+        if not (0 <= row0 and step >= 1 and n_rows >= 1 and grp >= 1 and
+                row0 + ((n_rows - 1) // grp) * step + (n_rows - 1) % grp < h):
+            raise ValueError("rows=(row0,row_step,n_rows[,row_group]) outside the image")
+        self.full_image = (row0 == 0 and step == grp and n_rows == h)
         self.local_hw = (n_rows, w)
         self.n_views = 1             # > 1 only on the children made by _fused_child (multi-view march, render_views)
         self.Pv = n_rows * w         # pixels per view
@@ -188,6 +209,12 @@ class SDFRenderer(object):
         # replay: forward + transposed chain) cost 2F
         self.rows_evaluated = torch.zeros(1, device=self.device, dtype=torch.int64)
         self.rows_grad = torch.zeros(1, device=self.device, dtype=torch.int64)
+        # 128-row tile programs of the forward launches evaluated with [one fp16 pass, three split-precision passes]
+        self.tile_counters = torch.zeros(2, device=self.device, dtype=torch.int64)
+        # two-tier precision of the march (dist_march_t.screen): on unless switched off here or by DIST_SCREEN=0
+        import os
+        self.screen = (os.environ.get("DIST_SCREEN", "1") != "0") if screen is None else bool(screen)
+        self.screen_tpred = float(os.environ.get("DIST_SCREEN_TPRED", screen_tpred))
         self._homo_calib = None
         self._calib_map = None
         self._scr = None
@@ -207,9 +234,8 @@ class SDFRenderer(object):
     def homo_calib(self):
         """K^-1 [x, y, 1] for the rendered rows, (3, P).  renderer.py:37-39."""
         if self._homo_calib is None:
-            row0, step, n_rows = self.rows
             w = self.img_hw[1]
-            ys = (row0 + step * torch.arange(n_rows, device=self.device)).float()
+            ys = self._image_rows(torch.arange(self.rows[2], device=self.device)).float()
             xs = torch.arange(w, device=self.device).float()
             Y, X = torch.meshgrid(ys, xs, indexing="ij")
             homo = torch.stack([X.reshape(-1), Y.reshape(-1), torch.ones(self.Pv, device=self.device)], 0)
@@ -264,6 +290,11 @@ class SDFRenderer(object):
         return torch.norm(cam_pos[:, None] - ptq[None, :] * cam_rays, p=2, dim=0)
 
     # ---- internals ------------------------------------------------------------------------------------------
+    def _image_rows(self, local_rows):
+        """Image row of each local row of this renderer's band (interleaved groups of `row_group` rows)."""
+        row0, step, _, grp = self.rows
+        return row0 + (local_rows // grp) * step + local_rows % grp
+
     def _c_camera(self, R, cam_pos, use_transform=True):
         cam = _abi.Camera()
         Kinv = np.linalg.inv(self.intrinsic).astype(np.float32).reshape(-1)
@@ -274,7 +305,7 @@ class SDFRenderer(object):
         cam._keep = (R, cam_pos)
         cam.R, cam.cam_pos = R.data_ptr(), cam_pos.data_ptr()
         cam.width, cam.height = self.img_hw[1], self.img_hw[0]
-        cam.row0, cam.row_step, cam.n_rows = self.rows
+        cam.row0, cam.row_step, cam.n_rows, cam.row_group = self.rows
         cam.radius = self.radius
         cam.n_views = self.n_views
         return cam
@@ -298,8 +329,9 @@ class SDFRenderer(object):
         """K^-1 [xc, yc, 1] of the pooled pixel centres of the 1/2 and 1/4 resolution levels (renderer.py:604-636)."""
         if getattr(self, "_chomo", None) is None:
             res = []
-            for (hh, ww), scale in zip(self._coarse_dims(), (2.0, 4.0)):
-                ys = scale * torch.arange(hh, device=self.device).float() + (scale - 1) / 2
+            for (hh, ww), scale in zip(self._coarse_dims(), (2, 4)):
+                # the `scale` fine rows pooled into one coarse row are consecutive image rows (bands: 4-row groups)
+                ys = self._image_rows(scale * torch.arange(hh, device=self.device)).float() + (scale - 1) / 2
                 xs = scale * torch.arange(ww, device=self.device).float() + (scale - 1) / 2
                 Y, X = torch.meshgrid(ys, xs, indexing="ij")
                 homo = torch.stack([X.reshape(-1), Y.reshape(-1), torch.ones(hh * ww, device=self.device)], 0)
@@ -332,19 +364,30 @@ class SDFRenderer(object):
                 "b_row": torch.empty(P * self.buffer_size, **i32), "b_pts": torch.empty(P * self.buffer_size, 3, **f32),
                 "b_coef": torch.empty(P * self.buffer_size, **f32), "b_dpts": torch.empty(P * self.buffer_size, 3, **f32),
                 "b_cnt": torch.empty(1, **i32),
+                # two-tier precision: 3 rotating per-tile hint arrays + per-half-tile one-pass flags
+                "tile_mode": torch.zeros(3 * ((P + 1 + 127) // 128), device=dev, dtype=torch.uint8),
+                "seg_approx": torch.zeros(2 * ((P + 1 + 127) // 128), device=dev, dtype=torch.uint8),
             }
+            # the exact re-query rows of the forward pass live in the backward replay scratch (free until backward)
+            self._scr.update(rq_idx=self._scr["b_row"], rq_pts=self._scr["b_pts"], rq_sdf=self._scr["b_coef"],
+                             rq_cnt=self._scr["b_cnt"])
             if pyramid:
                 return self._scratch(pyramid=True)
         return self._scr
 
-    def _raise_if_empty(self):
-        """renderer.py:214-215.  Reads one int back from the device, i.e. waits for the enqueued march."""
-        if int(self._last_counts[:, 0].min().item()) == 0:   # view_stat[v][0]: rays of view v alive at step 0
+    def _raise_if_empty(self, stat=None):
+        """renderer.py:214-215.  Reads view_stat back from the device, i.e. waits for the enqueued march."""
+        stat = self._last_counts.cpu() if stat is None else stat
+        if int(stat[:, 3].max()) != 0:
+            raise FloatingPointError("non-finite sdf during the march: the decoder's activations overflow the fp16 "
+                                     "operands of the tensor-core engine for this latent; use engine='simt'")
+        if int(stat[:, 0].min()) == 0:   # view_stat[v][0]: rays of view v alive at step 0
             raise ValueError('No valid depth.')
 
     def reset_row_counter(self):
         self.rows_evaluated.zero_()
         self.rows_grad.zero_()
+        self.tile_counters.zero_()
 
     def flops_per_row(self):
         """F = 2 * sum K_l N_l of the folded network (3,146,752 for the standard 8x512 spec)."""
@@ -361,14 +404,21 @@ class SDFRenderer(object):
             raise NotImplementedError("sample_index_type='%s' is not implemented (only 'min_abs')" % sample_index_type)
         if ray_marching_type == 'pyramid_recursive':
             self._coarse_steps()
-            if self.rows != (0, 1, self.img_hw[0]):
-                raise NotImplementedError("pyramid_recursive needs the full image (row bands use 'recursive')")
+            if not self.full_image and self.rows[3] % 4 != 0:
+                raise NotImplementedError("pyramid_recursive on a row band needs bands of 4-row groups "
+                                          "(rows=(row0,row_step,n_rows,4)); single-row bands use 'recursive'")
         if ray_marching_type not in _MARCH:
             raise ValueError('Error! Invalid type of ray marching: {}.'.format(ray_marching_type))  # renderer.py:834
         any_grad = torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (latent, R, T))
+        # which samples keep their camera graph (dist_march_t.cam_grad_levels): no_grad_camera only detaches the points
+        # of ray_marching_recursive (renderer.py:536-537,543-544); ray_marching_trivial -- also the coarse levels of the
+        # pyramid -- never does (renderer.py:481-484), a quirk the reference's gradients carry and these reproduce
+        cam_levels = 3
+        if no_grad_camera:
+            cam_levels = {"recursive": 0, "pyramid_recursive": 2}.get(ray_marching_type, 3)
         opts = dict(kind=ray_marching_type, clamp_dist=clamp_dist, use_transform=use_transform, engine=self.engine,
                     want_depth_grad=any_grad and not no_grad_depth, want_mask_grad=any_grad and not no_grad_mask,
-                    want_camera_grad=any_grad and not no_grad_camera, replay=not no_grad_depth)
+                    cam_levels=cam_levels if any_grad else 0, replay=not no_grad_depth)
         Zdepth, mask, min_sdf, hit = _RenderDepthFn.apply(latent, R, T, self, opts)
         if check_empty:
             self._raise_if_empty()
@@ -387,9 +437,46 @@ class SDFRenderer(object):
                       normalize=True, use_transform=True):
         """Znormal (3, P): analytic decoder input-gradient at the hit points -- renderer.py:880-910.
 
-        The gradient of a ReLU / weight-norm decoder is piecewise constant, so the reference's autograd path
-        through this tensor to latent / T is zero; the returned tensor carries no graph."""
-        lib, st = _abi.lib(), _stream()
+        Autograd connectivity.  The input gradient of a ReLU / weight-norm decoder is
+        (1 - sdf^2) * a with `a` piecewise constant in (xyz, latent), so:
+          * normalize=True (default): the unit normal is piecewise constant -- the reference's graph through this
+            tensor to latent / R / T carries exact zeros, and the tensor returned here carries no graph;
+          * normalize=False with gradients enabled (and not no_grad): the factor (1 - sdf^2) does depend on latent and,
+            through the hit point p = M^T (c + ray * z), on R and T (z detached, renderer.py:211-212).  It is attached
+            as the value-neutral multiplier f(sdf) / f(sdf).detach() with f = d tanh-chain / d pre-activation, the sdf
+            being re-queried differentiably on the hit rows (one extra forward row + one backward-replay row per hit
+            pixel), which reproduces the reference's second-order term without a second-order graph."""
+        with torch.cuda.device(self.device):
+            Znormal, n_idx = self._render_normal_raw(latent, R, T, Zdepth, valid_mask, clamp_dist, normalize,
+                                                     use_transform)
+            want_graph = (not normalize) and (not no_grad) and torch.is_grad_enabled() and \
+                any(t is not None and t.requires_grad for t in (latent, R, T))
+            if not want_graph:
+                return Znormal
+            from .functional import decode_sdf
+            idx = torch.nonzero(valid_mask.reshape(-1).bool()).reshape(-1)
+            if idx.numel() == 0:
+                return Znormal
+            v = idx // self.Pv if R.dim() == 3 else None
+            cam_pos, cam_rays = self.get_camera_location(R, T), self.get_camera_rays(R)
+            if v is None:
+                pts = cam_rays[:, idx] * Zdepth.detach()[idx][None, :] + cam_pos[:, None]
+            else:   # stacked poses: (V,3,Pv) rays, (V,3) centres
+                pts = cam_rays[v, :, idx - v * self.Pv].t() * Zdepth.detach()[idx][None, :] + cam_pos[v].t()
+            if use_transform:
+                pts = self.inv_transform_points(pts)
+            o = decode_sdf(self.decoder, latent, pts.t(), clamp_dist=None, engine=self.engine).squeeze(-1)
+
+            def dchain(x):     # d sdf / d pre-activation as a function of the sdf value (deep_sdf_decoder.py:99-110)
+                if self.plan.use_tanh:
+                    return (1 - x * x) * (1 - torch.atanh(x) ** 2)
+                return 1 - x * x
+            factor = dchain(o) / dchain(o.detach())
+            scale = torch.ones(self.P, device=self.device, dtype=torch.float32).index_copy(0, idx, factor)
+            return Znormal * scale[None, :]
+
+    def _render_normal_raw(self, latent, R, T, Zdepth, valid_mask, clamp_dist, normalize, use_transform):
+        lib, st = _abi.lib(), _stream(self.device)
         plan = self.plan
         plan.refresh()
         engine = resolve_engine(plan, self.engine)
@@ -405,7 +492,7 @@ class SDFRenderer(object):
                                               1 if normalize else 0, _abi.ptr(Znormal), _abi.ptr(scr["n_idx"]),
                                               _abi.ptr(scr["n_pts"]), _abi.ptr(scr["n_grad"]), _abi.ptr(scr["n_cnt"]),
                                               _abi.ptr(self.rows_grad), st))
-        return Znormal
+        return Znormal, scr["n_idx"]
 
     def render(self, latent, R, T, clamp_dist=0.1, sample_index_type='min_abs', profile=False, no_grad=False,
                no_grad_depth=False, no_grad_normal=False, no_grad_mask=False, no_grad_camera=False,
@@ -446,7 +533,7 @@ class SDFRenderer(object):
             if num_forward_sampling != 0:
                 raise NotImplementedError("forward sampling is not available on the multi-view march")
             # pose by pose with the single-pose GEMM on contiguous operands: a batched GEMM may round differently
-            Rn, n3 = (R if not no_grad_normal else R.detach()), normal.reshape(3, V, -1)
+            Rn, n3 = R, normal.reshape(3, V, -1)   # renderer.py:977-978: no_grad_normal detaches Znormal, never R
             normal = torch.stack([torch.matmul(Rn[v], n3[:, v].contiguous()) for v in range(V)], 0)   # renderer.py:978
             normal = torch.cat([normal[:, :1] * (-1), normal[:, 1:]], 1).reshape(V, 3, h, w).permute(0, 2, 3, 1)
             out = (depth.reshape(V, h, w), normal, valid_mask.reshape(V, h, w).type(torch.uint8),
@@ -454,7 +541,7 @@ class SDFRenderer(object):
             if check_empty:
                 self._raise_if_empty()
             return out
-        normal = torch.matmul(R if not no_grad_normal else R.detach(), normal)  # renderer.py:978
+        normal = torch.matmul(R, normal)  # renderer.py:978 (no_grad_normal detaches Znormal only, renderer.py:909)
         normal = torch.cat([normal[:1] * (-1), normal[1:]], 0)                   # renderer.py:979
         normal = normal.reshape(3, h, w).permute(1, 2, 0)
         out = (depth.reshape(h, w), normal, valid_mask.reshape(h, w).type(torch.uint8), min_abs_query.reshape(h, w))

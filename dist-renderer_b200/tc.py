@@ -19,6 +19,7 @@ import torch
 
 from . import _abi
 
+SCREEN_MARGIN = 2e-3  # two-tier precision: a one-pass sdf beyond clamp + margin is "far"; one-pass error must be < margin / 2
 S_ACT = 32.0        # activation scale (power of two): post-ReLU activations up to ~2000 stay finite in fp16
 S_GRAD = 256.0      # scale of the backward-chain operand (d sdf / d pre-activation, unit seed)
 
@@ -82,17 +83,17 @@ def _tiles(w, scale, c_trunc):
     return both.contiguous().reshape(-1), kc, NH
 
 
-_C_TRUNC = None     # measured per-accumulation truncation loss of the tcgen05 fp32 accumulator (see _tiles)
+_C_TRUNC = {}       # device index -> measured per-accumulation truncation loss of the tcgen05 fp32 accumulator (_tiles)
 
 
 def calibrate(plan, n_points=8192):
     """Measures the truncation constant c on this device: the final-sdf deviation of the tensor-core engine from the
     exact-fp32 SIMT engine is linear in the compensation constant, so two probes (c = 0 and c = c1) give its root."""
-    global _C_TRUNC
-    if _C_TRUNC is not None:
-        return _C_TRUNC
+    dev_key = plan.device.index if plan.device.index is not None else torch.cuda.current_device()
+    if dev_key in _C_TRUNC:
+        return _C_TRUNC[dev_key]
     lib = _abi.lib()
-    st = torch.cuda.current_stream().cuda_stream
+    st = torch.cuda.current_stream(plan.device).cuda_stream
     g = torch.Generator().manual_seed(1234)
     pts = ((torch.rand(n_points, 3, generator=g) - 0.5) * 1.2).to(plan.device)
     lat = torch.zeros(plan.latent_size, device=plan.device) if plan.latent_size > 0 else None
@@ -113,10 +114,13 @@ def calibrate(plan, n_points=8192):
     c1 = 4.0e-8
     e0, e1 = probe(0.0), probe(c1)
     plan.tc = saved
+    if not (math.isfinite(e0) and math.isfinite(e1)):
+        # this decoder overflows the fp16 operands: nothing was measured, so nothing is cached for the device
+        raise NotImplementedError("tensor-core calibration probes are not finite for this decoder")
     c = c1 * e0 / (e0 - e1) if abs(e0 - e1) > 1e-12 else 0.0
     if not (0.0 <= c <= 4.0e-7):      # outside anything physical: do not compensate
         c = 0.0
-    _C_TRUNC = c
+    _C_TRUNC[dev_key] = c
     return c
 
 
@@ -126,9 +130,21 @@ def prepare(plan):
         return plan.tc
     if not supported(plan):
         raise NotImplementedError("the tensor-core engine does not cover this decoder shape / device")
-    c = calibrate(plan)
-    plan.tc = _build(plan, c)
-    _self_check(plan)
+    with torch.cuda.device(plan.device):
+        dev_key = plan.device.index if plan.device.index is not None else torch.cuda.current_device()
+        if dev_key not in _C_TRUNC:
+            # the truncation constant is a property of the device, measured once -- but only through a decoder whose
+            # operands provably fit fp16: self-check the uncompensated operands first (the bias being calibrated away is
+            # ~5e-6, far below the self-check tolerance), then calibrate
+            plan.tc = _build(plan, 0.0)
+            _self_check(plan)
+            try:
+                calibrate(plan)
+            except NotImplementedError:
+                _mark_unsafe(plan, float("nan"))
+        plan.tc = _build(plan, _C_TRUNC[dev_key])
+        _self_check(plan)
+        plan.tc["screen"] = _screen_check(plan)
     return plan.tc
 
 
@@ -137,7 +153,7 @@ def _self_check(plan, n_points=4096, tol=2e-5):
     decoder's own rows (activations beyond ~2000 or non-finite values would overflow the fp16 operands).  On failure
     the plan is marked unsafe: 'auto' then resolves to the fp32 engine and engine='tc' raises."""
     lib = _abi.lib()
-    st = torch.cuda.current_stream().cuda_stream
+    st = torch.cuda.current_stream(plan.device).cuda_stream
     g = torch.Generator().manual_seed(4321)
     pts = ((torch.rand(n_points, 3, generator=g) - 0.5) * 2.0).to(plan.device)
     lat = (0.1 * torch.randn(plan.latent_size, generator=g)).to(plan.device) if plan.latent_size > 0 else None
@@ -150,12 +166,47 @@ def _self_check(plan, n_points=4096, tol=2e-5):
     _abi.check(lib.dist_decoder_forward(net, _abi.ENGINE_TC, _abi.ptr(pts), n_points, None, 0.0, _abi.ptr(out), st))
     err = float((out - ref).abs().max())
     if not (err < tol):
+        _mark_unsafe(plan, err)
+
+
+def _screen_check(plan, n_points=8192):
+    """Two-tier precision of the march (dist_march_t.screen): rows whose sdf is safely beyond the clamp are evaluated with
+    ONE fp16 pass.  Measures, on a sample of this decoder's own rows, how far the one-pass value is from the
+    three-pass one; the scheme is enabled for the plan only if the worst deviation is below SCREEN_MARGIN / 4 (the
+    kernels assume an error bound of SCREEN_MARGIN / 2).  Returns {'margin', 'err'} or None (screening off, warned)."""
+    lib = _abi.lib()
+    st = torch.cuda.current_stream(plan.device).cuda_stream
+    g = torch.Generator().manual_seed(977)
+    pts = ((torch.rand(n_points, 3, generator=g) - 0.5) * 2.0).to(plan.device)
+    lat = (0.1 * torch.randn(plan.latent_size, generator=g)).to(plan.device) if plan.latent_size > 0 else None
+    b0, bl, _ = plan.fold(lat, st)
+    net = plan.c_net(b0, bl, bl * S_ACT if bl is not None else None)
+    exact = torch.empty(n_points, device=plan.device)
+    one = torch.empty(n_points, device=plan.device)
+    tiles = (n_points + 127) // 128
+    mode = torch.zeros(tiles, device=plan.device, dtype=torch.uint8)
+    seg = torch.zeros(2 * tiles, device=plan.device, dtype=torch.uint8)
+    _abi.check(lib.dist_decoder_forward(net, _abi.ENGINE_TC, _abi.ptr(pts), n_points, None, 0.0, _abi.ptr(exact), st))
+    # threshold -1: no |sdf| is <= -1, so every half-tile keeps its one-pass values
+    _abi.check(lib.dist_decoder_forward_tiers(net, _abi.ptr(pts), n_points, None, _abi.ptr(mode), -1.0, _abi.ptr(one),
+                                              _abi.ptr(seg), None, st))
+    err = float((one - exact).abs().max())
+    ok = bool(seg.bool().all()) and err < SCREEN_MARGIN / 4
+    if not ok:
         import warnings
-        plan.tc = None
-        plan.tc_unsafe = True
-        warnings.warn("dist-renderer_b200: tensor-core engine disabled for this decoder (max |tc - fp32| = %g on a "
-                      "self-check sample: operand range exceeds fp16); using the fp32 engine" % err)
-        raise NotImplementedError("tensor-core engine failed its self-check for this decoder")
+        warnings.warn("dist-renderer_b200: two-tier precision disabled for this decoder (one-pass sdf deviates by %g, "
+                      "limit %g): every march row runs at full split precision" % (err, SCREEN_MARGIN / 4))
+        return None
+    return {"margin": SCREEN_MARGIN, "err": err}
+
+
+def _mark_unsafe(plan, err):
+    import warnings
+    plan.tc = None
+    plan.tc_unsafe = True
+    warnings.warn("dist-renderer_b200: tensor-core engine disabled for this decoder (max |tc - fp32| = %g on a "
+                  "self-check sample: operand range exceeds fp16); using the fp32 engine" % err)
+    raise NotImplementedError("tensor-core engine failed its self-check for this decoder")
 
 
 def _build(plan, c_trunc):

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define DIST_ABI_VERSION 1
+#define DIST_ABI_VERSION 2
 #define DIST_MAX_LAYERS 16
 #define DIST_MAX_WIDTH 512
 #define DIST_MAX_BUFFER 8      /* max buffer_size (samples kept per ray) */
@@ -85,7 +85,7 @@ typedef struct dist_camera {
   int32_t width;              /* full image width */
   int32_t height;             /* full image height */
   int32_t row0;               /* first image row rendered by this call (ray-tile sharding) */
-  int32_t row_step;           /* stride between rendered rows (interleaved bands) */
+  int32_t row_step;           /* image rows between the starts of consecutive row groups (interleaved bands) */
   int32_t n_rows;             /* number of rows rendered; local pixel lp = lrow*width + x */
   float radius;               /* unit-sphere radius (renderer.py:23) */
   int32_t n_views;            /* views of the same shape marched by ONE call (0 or 1: a single view).  All per-pixel
@@ -93,6 +93,10 @@ typedef struct dist_camera {
                                  optimize_multi.py:62-80 / renderer_warp.py:108-109 become one march, one compaction
                                  list, one tail.  Each view keeps the per-render semantics of the reference (its own
                                  early break, 'No valid depth' test, pyramid levels). */
+  int32_t row_group;          /* rows per interleaved group (0 or 1: single rows): local row l is image row
+                                 row0 + (l / row_group) * row_step + l % row_group.  DIST_MARCH_PYRAMID on a band needs
+                                 row_group % 4 == 0, which keeps the 1/2- and 1/4-resolution levels band-local
+                                 (SURVEY 8e); the last group of a band may be shorter (image height not a multiple). */
 } dist_camera_t;
 
 /* March parameters (renderer.py:13 ctor arguments + render_depth arguments). */
@@ -106,6 +110,19 @@ typedef struct dist_march {
   float clamp_dist;
   int32_t replay_grad_rounding; /* 1: reproduce the value-neutral (z - a) + a roundings of renderer.py:414-417 */
   int32_t coarse_steps[2];    /* DIST_MARCH_PYRAMID: trivial steps at 1/4 and 1/2 resolution (renderer.py:13 march_step_list) */
+  int32_t screen;             /* two-tier precision of the march on DIST_ENGINE_TC (0 = every row at full precision): a row
+                                 whose sdf is safely beyond the clamp, |sdf| > clamp_dist + screen_margin, steps by exactly
+                                 ratio * clamp_dist whatever its last bits are (renderer.py:548-551), so 128-row tiles are
+                                 first evaluated with ONE fp16 tensor-core pass and only tiles with a nearer row are
+                                 re-evaluated with the three split-precision passes; the value of a one-pass sample is
+                                 only ever used where the reference's result does not depend on it, except a ray's
+                                 smallest |sdf|, which is re-queried at full precision before the maps are written */
+  float screen_margin;        /* one-pass values must be accurate to screen_margin / 2 (checked at prepare time) */
+  float screen_tpred;         /* tiles with a row whose previous |sdf| was <= screen_tpred skip the one-pass attempt */
+  int32_t cam_grad_levels;    /* dist_render_depth_bwd: which samples carry a camera gradient -- bit 0: samples of the
+                                 full-resolution march, bit 1: samples inherited from the coarse pyramid levels
+                                 (0 = both).  no_grad_camera detaches only the points of ray_marching_recursive
+                                 (renderer.py:536-537); ray_marching_trivial never detaches (renderer.py:481-484) */
 } dist_march_t;
 
 /*
@@ -132,16 +149,28 @@ typedef struct dist_workspace {
   float* sdf_origin; /* [1] sdf at the origin (filler samples, renderer.py:539-540) */
   float* entry0;     /* [P] true unit-sphere entry depth; == entry except in DIST_MARCH_PYRAMID, where `entry` holds the
                         depth the full-resolution march starts from (inherited from the 1/2-resolution parent ray) */
-  uint8_t* top_lvl;  /* [B][P] pyramid level the sample was taken at (0 = this ray; 1, 2 = parent / grandparent ray) */
+  uint8_t* top_lvl;  /* [B][P] bits 0-1: pyramid level the sample was taken at (0 = this ray; 1, 2 = parent / grandparent
+                        ray); bit 7: the recorded sdf is a one-pass value; bit 6: it was re-queried at full precision */
   /* DIST_MARCH_PYRAMID only (renderer.py:713-805).  With (w1,h1) = ceil((w,h)/2), (w2,h2) = ceil((w1,h1)/2),
    * P1 = w1*h1, P2 = w2*h2:  pyr_f: 23*(P1+P2) floats, pyr_i: (P1+P2)+8 int32, pyr_b: (P1+P2) bytes. */
   float* pyr_f;      /* (all three scale with n_views) */
   int32_t* pyr_i;
   uint8_t* pyr_b;
+  /* two-tier precision (dist_march_t.screen; all NULL otherwise).  T = ceil((P+1)/128): */
+  uint8_t* tile_mode;   /* [3][T] per-step tile hints, rotating (written one step ahead by the march update); zeroed by
+                           dist_render_depth_fwd */
+  uint8_t* seg_approx;  /* [2T] per 64-row half-tile of the current step: 1 = one-pass values */
+  int32_t* rq_idx;      /* [P*B] re-query rows: local pixel * DIST_MAX_BUFFER + record slot */
+  float* rq_pts;        /* [P*B][3] */
+  float* rq_sdf;        /* [P*B] */
+  int32_t* rq_cnt;      /* [1] */
+  unsigned long long* tile_counters; /* optional [2], accumulated: 128-row tile programs evaluated with one fp16 pass /
+                           with three (a gradient tile counts two programs: forward + transposed chain) */
   int32_t* view_stat; /* [n_views][4] per-view bookkeeping, zeroed by dist_render_depth_fwd: [0] rays alive at step 0
                          (0 <=> the reference raises 'No valid depth', renderer.py:214), [1] march steps the view
                          executed before its early break (renderer.py:562), [2] float bits of the largest coarse-level
-                         sphere entry (renderer.py:270-272), [3] reserved */
+                         sphere entry (renderer.py:270-272), [3] != 0: a decoder output of the march was not in
+                         [-1, 1] (NaN / inf: operand overflow of the fp16 tensor-core engine) */
 } dist_workspace_t;
 
 /* ---- library ---- */
@@ -168,6 +197,16 @@ int dist_fold_latent(const dist_net_t* net, const float* latent, float* out0, fl
  * clamp_dist <= 0 means no clamp.  Replaces decode_sdf (decoder_utils.py:53-74). */
 int dist_decoder_forward(const dist_net_t* net, int engine, const float* points, int64_t n_host,
                          const int32_t* n_dev, float clamp_dist, float* sdf, void* stream);
+
+/* dist_decoder_forward on the tensor-core engine with the two-tier precision the march uses (dist_march_t.screen), exposed
+ * for the prepare-time accuracy check of the one-pass values and for tests: tile_mode[ceil(n/128)] (0 = try one fp16 pass
+ * first, != 0 = three split-precision passes); a 64-row half-tile keeps its one-pass values when all of its rows have
+ * |sdf| > screen_thresh, and is flagged in seg_approx[ceil(n/64)] (1 = one-pass values); all other rows are bit-identical
+ * to dist_decoder_forward.  tile_counters (optional, [2]) += tile programs evaluated with one / three passes.
+ * No counterpart in the reference: its decoder (deep_sdf_decoder.py:80-111) is fp32 throughout. */
+int dist_decoder_forward_tiers(const dist_net_t* net, const float* points, int64_t n_host, const int32_t* n_dev,
+                               const uint8_t* tile_mode, float screen_thresh, float* sdf, uint8_t* seg_approx,
+                               unsigned long long* tile_counters, void* stream);
 
 /* grad[i] = d clamp(sdf)/d xyz at points[i]; sdf (optional) receives the clamped value.
  * Replaces decode_sdf_gradient (decoder_utils.py:76-92). */

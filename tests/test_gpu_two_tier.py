@@ -1,0 +1,108 @@
+"""GPU: two-tier precision of the march rows on the tensor-core engine (dist_march_t.screen, csrc/mlp_tc.cu).
+
+Rows whose sdf is safely beyond the march's clamp are evaluated with ONE fp16 tensor-core pass; everything the
+reference's results depend on (rows inside the clamp band, each ray's smallest |sdf|) is evaluated with the three
+split-precision passes.  So a screened render must equal the unscreened one, and the kernel-level contract of
+dist_decoder_forward_tiers must hold row by row.
+"""
+import importlib
+
+import pytest
+import torch
+
+import cases
+import gpu_util as gu
+
+pytestmark = pytest.mark.gpu
+pkg = cases.pkg
+synth = cases.synth
+abi = importlib.import_module("dist-renderer_b200._abi")
+tc = importlib.import_module("dist-renderer_b200.tc")
+plan_mod = importlib.import_module("dist-renderer_b200.plan")
+
+
+def _tiers(plan, lat, pts, mode, thresh):
+    lib, st = abi.lib(), torch.cuda.current_stream().cuda_stream
+    tc.prepare(plan)
+    b0, bl, _ = plan.fold(lat, st)
+    net = plan.c_net(b0, bl, bl * tc.S_ACT if bl is not None else None)
+    n = pts.shape[0]
+    sdf = torch.full((n,), float("nan"), device="cuda")
+    seg = torch.full(((n + 63) // 64,), 7, device="cuda", dtype=torch.uint8)
+    cnt = torch.zeros(2, device="cuda", dtype=torch.int64)
+    abi.check(lib.dist_decoder_forward_tiers(net, abi.ptr(pts), n, None, abi.ptr(mode), float(thresh), abi.ptr(sdf),
+                                             abi.ptr(seg), abi.ptr(cnt), st))
+    return sdf, seg, cnt
+
+
+@pytest.mark.parametrize("n", [128 * 300 + 37, 128 * 74 * 3, 100])
+def test_tiers_kernel_contract(n):
+    dec = gu.gpu_decoder("B")
+    plan = plan_mod.plan_for(dec)
+    lat = synth.make_latent().cuda()
+    g = torch.Generator().manual_seed(5)
+    pts = (torch.rand(n, 3, generator=g) - 0.5) * 1.6
+    pts = pts[pts.norm(dim=1).argsort()].contiguous().cuda()     # radius order: coherent tiles, some all far, some mixed
+    exact = pkg.decode_sdf(dec, lat, pts, clamp_dist=None, no_grad=True, engine="tc").reshape(-1)
+    tiles = (n + 127) // 128
+    thresh = 0.102
+    # (a) every tile tries one pass first
+    sdf, seg, cnt = _tiers(plan, lat, pts, torch.zeros(tiles, device="cuda", dtype=torch.uint8), thresh)
+    assert int(seg.max()) <= 1
+    row_approx = seg.repeat_interleave(64)[:n].bool()
+    assert bool(torch.equal(sdf[~row_approx], exact[~row_approx]))          # full-precision rows: bit-identical
+    if bool(row_approx.any()):
+        assert float(exact[row_approx].abs().min()) > 0.1                   # one-pass values only beyond the clamp
+        assert float((sdf[row_approx] - exact[row_approx]).abs().max()) < tc.SCREEN_MARGIN / 2
+    pad = (-n) % 128
+    far_tile = torch.cat([exact.abs() > thresh + tc.SCREEN_MARGIN, torch.ones(pad, dtype=torch.bool, device="cuda")]).reshape(-1, 128).all(1)
+    seg_tile = torch.cat([seg, seg.new_ones(2 * tiles - seg.numel())]).reshape(-1, 2).bool().all(1)
+    assert bool(seg_tile[far_tile].all())                                    # clearly far tiles keep their one-pass values
+    assert int(cnt[0]) == tiles and int(cnt[1]) == int((~seg_tile).sum())    # failed tiles are redone, once
+    # (b) hints say "near": three passes directly, nothing flagged
+    sdf, seg, cnt = _tiers(plan, lat, pts, torch.ones(tiles, device="cuda", dtype=torch.uint8), thresh)
+    assert bool(torch.equal(sdf, exact)) and int(seg.max()) == 0 and cnt.tolist() == [0, tiles]
+    # (c) mixed hints
+    mode = (torch.arange(tiles, device="cuda") % 3 == 0).to(torch.uint8)
+    sdf, seg, cnt = _tiers(plan, lat, pts, mode, thresh)
+    row_approx = seg.repeat_interleave(64)[:n].bool()
+    assert bool(torch.equal(sdf[~row_approx], exact[~row_approx]))
+    seg_full = torch.cat([seg, seg.new_zeros(2 * tiles - seg.numel())]).reshape(-1, 2)
+    assert not bool(seg_full[mode.bool()].any())                              # hinted tiles are never one-pass
+
+
+@pytest.mark.parametrize("kind", ["recursive", "pyramid_recursive", "trivial"])
+@pytest.mark.parametrize("hw,cam", [((160, 160), ("front", 1.6)), ((96, 130), ("lookat", 40.0, 25.0, 2.5, 1.2 * 2.5 / 1.6))])
+def test_screened_render_equals_full_precision_render(kind, hw, cam):
+    """Same trajectories, same selected samples, same maps: the one-pass values never reach an output."""
+    dec = gu.gpu_decoder("B")
+    K, R, T = cases.camera(cam, hw)
+    lat0, R, T = synth.make_latent().cuda(), R.cuda(), T.cuda()
+    outs, grads, counters = [], [], []
+    for screen in (True, False):
+        ren = pkg.SDFRenderer(dec, K, img_hw=hw, march_step=50, buffer_size=5, engine="tc", screen=screen)
+        lat = lat0.clone().requires_grad_(True)
+        Rg, Tg = R.clone().requires_grad_(True), T.clone().requires_grad_(True)
+        out = ren.render(lat, Rg, Tg, ray_marching_type=kind)
+        cases.scalar_loss(out).backward()
+        outs.append([o.detach() for o in out])
+        grads.append((lat.grad, Rg.grad, Tg.grad))
+        counters.append(ren.tile_counters.tolist())
+    assert counters[0][0] > 0 and counters[1][0] == 0, counters       # the screened run did use one-pass tiles
+    print(kind, hw, "tile programs [1-pass, 3-pass]: screened", counters[0], "full", counters[1])
+    for name, a, b in zip(("depth", "normal", "mask", "min_sdf"), outs[0], outs[1]):
+        assert torch.equal(a, b), (name, int((a != b).sum()), float((a.float() - b.float()).abs().max()))
+    for a, b in zip(grads[0], grads[1]):
+        assert gu.rel(a, b) < 1e-5
+
+
+def test_screen_can_be_disabled_and_is_off_for_simt():
+    dec = gu.gpu_decoder("B")
+    K, (R, T) = synth.intrinsic(64, 64), synth.front_camera()
+    lat, R, T = synth.make_latent().cuda(), R.cuda(), T.cuda()
+    r0 = pkg.SDFRenderer(dec, K, img_hw=(64, 64), engine="simt")
+    r0.render(lat, R, T, ray_marching_type="recursive", no_grad=True)
+    assert r0.tile_counters.tolist() == [0, 0]
+    r1 = pkg.SDFRenderer(dec, K, img_hw=(64, 64), engine="tc", screen=False)
+    r1.render(lat, R, T, ray_marching_type="recursive", no_grad=True)
+    assert r1.tile_counters[0].item() == 0 and r1.tile_counters[1].item() > 0

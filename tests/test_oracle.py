@@ -16,7 +16,8 @@ def _rel(a, b):
     return float((a - b).norm() / (b.norm() + 1e-300))
 
 
-def _run_oracle(cs, dtype=torch.float32):
+def _run_oracle(cs, dtype=torch.float32, flags=None):
+    flags = flags or {}
     dec = cases.decoder(cs["decoder"])
     if dtype == torch.float64:
         import copy
@@ -26,9 +27,9 @@ def _run_oracle(cs, dtype=torch.float32):
                             dtype=dtype)
     lat = cases.synth.make_latent().to(dtype).requires_grad_(True)
     Rg, Tg = R.to(dtype).requires_grad_(True), T.to(dtype).requires_grad_(True)
-    out = ren.render(lat, Rg, Tg, ray_marching_type=cs["kind"])
+    out = ren.render(lat, Rg, Tg, ray_marching_type=cs["kind"], **flags)
     cases.scalar_loss(out).backward()
-    return out, (lat.grad, Rg.grad, Tg.grad)
+    return out, tuple(t.grad if t.grad is not None else torch.zeros_like(t) for t in (lat, Rg, Tg))
 
 
 @pytest.mark.parametrize("name", sorted(cases.CASES))
@@ -46,6 +47,57 @@ def test_oracle_matches_golden(name):
     assert _rel(out[3].detach().numpy(), gold["min_sdf"]) < 1e-6
     for g, key in zip(grads, ("g_latent", "g_R", "g_T")):
         assert _rel(g.numpy(), gold[key]) < 1e-4, key
+
+
+@pytest.mark.parametrize("name", sorted(cases.FLAG_CASES))
+def test_oracle_matches_flag_golden(name):
+    """One fixture per gradient flag of the reference's render() (renderer.py:943-957): which of d latent / dR / dT
+    survive each flag -- including the reference's quirk that the trivial march (and with it the coarse levels of the
+    pyramid) ignores no_grad_camera (renderer.py:481-484 never detaches its points)."""
+    cs = cases.FLAG_CASES[name]
+    gold = np.load(os.path.join(cases.GOLDEN_DIR, name + ".npz"))
+    out, grads = _run_oracle(cs, flags=cs["flags"])
+    assert int((out[2].numpy() != gold["mask"]).sum()) == 0
+    m = gold["mask"].astype(bool)
+    assert _rel(out[0].detach().numpy()[m], gold["depth"][m]) < 1e-6
+    assert _rel(out[1].detach().numpy(), gold["normal"]) < 1e-5
+    assert _rel(out[3].detach().numpy(), gold["min_sdf"]) < 1e-6
+    for g, key in zip(grads, ("g_latent", "g_R", "g_T")):
+        ref = gold[key]
+        if float(np.abs(ref).max()) < 1e-6:
+            assert float(g.abs().max()) < 1e-6, key
+        else:
+            assert _rel(g.numpy(), ref) < 1e-4, key
+
+
+@pytest.mark.parametrize("name", ["earlybreak_recursive_16", "earlybreak_pyramid_16"])
+def test_oracle_earlybreak_padding_render_depth(name):
+    """renderer.py:562-567: when every ray finishes in fewer than buffer_size steps the lists are padded with copies of
+    the last step; visible in render_depth's raw Zdepth and in the gradient through all buffer_size samples."""
+    cs = cases.CASES[name]
+    gold = np.load(os.path.join(cases.GOLDEN_DIR, name + ".npz"))
+    K, R, T = cases.camera(cs["cam"], cs["hw"])
+    ren = OracleSDFRenderer(cases.decoder(cs["decoder"]), K, img_hw=cs["hw"], march_step=cs["march_step"],
+                            buffer_size=cs["buffer_size"])
+    lat = cases.synth.make_latent().requires_grad_(True)
+    Rg, Tg = R.clone().requires_grad_(True), T.clone().requires_grad_(True)
+    Zd, _, _ = ren.render_depth(lat, Rg, Tg, ray_marching_type=cs["kind"])
+    Zd[Zd < 1e10].sum().backward()
+    assert _rel(Zd.detach().numpy(), gold["rd_Zdepth"]) < 1e-6
+    for g, key in zip((lat.grad, Rg.grad, Tg.grad), ("rd_g_latent", "rd_g_R", "rd_g_T")):
+        assert _rel(g.numpy(), gold[key]) < 1e-4, key
+
+
+def test_big_fixtures_present_and_consistent():
+    """The BASELINE-size fixtures (cases.BIG_CASES; written by `oracle/make_golden.py --big` from the real reference)
+    are too slow to re-render in the CPU suite: check they exist, match the seeded decoder and carry their fp64 floor."""
+    for name, cs in cases.BIG_CASES.items():
+        gold = np.load(os.path.join(cases.GOLDEN_DIR, "big_" + name + ".npz"))
+        assert abs(cases.weights_checksum(cases.decoder(cs["decoder"])) - float(gold["weights_checksum"])) < 1e-6
+        assert gold["depth"].shape == cs["hw"] and gold["normal"].shape == cs["hw"] + (3,)
+        assert gold["mask"].dtype == np.uint8 and 0.05 < gold["mask"].mean() < 0.6
+        floor = dict(zip(gold["floor_keys"].tolist(), gold["floor_vals"].tolist()))
+        assert floor["depth"] < 1e-5 and floor["xor"] <= 0.0005 * gold["mask"].size, floor
 
 
 def test_oracle_decoder_points_golden():
@@ -252,7 +304,7 @@ def test_deepsdf_sampler_host_logic_matches_live_reference(monkeypatch):
     RT = torch.cat([R, T[:, None]], 1)
     ref = Deep(ref_dec, K, img_hw=hw, use_gpu=False)
     prod = object.__new__(mod.SDFRenderer_deepsdf)            # no CUDA here: set what the camera helpers read
-    prod.decoder, prod.device, prod.img_hw, prod.rows, prod.Pv = dec, torch.device("cpu"), hw, (0, 1, hw[0]), hw[0] * hw[1]
+    prod.decoder, prod.device, prod.img_hw, prod.rows, prod.Pv = dec, torch.device("cpu"), hw, (0, 1, hw[0], 1), hw[0] * hw[1]
     prod.K_inv = torch.from_numpy(np.linalg.inv(K)).float()
     prod.transform_matrix = torch.tensor([[1., 0., 0.], [0., 0., -1.], [0., 1., 0.]])
     prod._homo_calib = prod._calib_map = None

@@ -30,25 +30,32 @@ def _full_image(H, W):
     return depth, normal, mask, min_sdf
 
 
+def _band_rows(H, rank, world):
+    """Image rows of `rank`'s band, spelled out independently of parallel.band: 4-row groups rank, rank+world, ..."""
+    return [y for y in range(H) if (y // 4) % world == rank]
+
+
 def _worker(rank, world, port, H, W, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     full = _full_image(H, W)
-    row0, step, n_rows = par.band(H, rank, world)
-    assert n_rows == len(range(rank, H, world))
-    local = tuple(t[row0::step] for t in full)
+    rows = _band_rows(H, rank, world)
+    assert par.band(H, rank, world)[2] == len(rows)
+    local = tuple(t[rows] for t in full)
     extra = torch.full((5,), float(rank + 1))
-    outs, extras = par.gather_bands(local, (H, W), rank, world, extra=extra)
-    ok = all(torch.equal(a.float(), b.float()) for a, b in zip(outs, full))
-    ok = ok and outs[2].dtype == torch.uint8 and extras.shape == (world, 5)
+    stat = torch.tensor([[10 * rank + 1, rank, 7, 0]], dtype=torch.int32)
+    outs, stats, extras = par.gather_bands(local, (H, W), rank, world, stat=stat, extra=extra)
+    ok = all(torch.equal(a, b) for a, b in zip(outs, full))          # bit-exact, dtypes included (mask stays uint8)
+    ok = ok and outs[2].dtype == torch.uint8 and extras.shape == (world, 5) and stats.shape == (world, 4)
+    ok = ok and stats[:, 0].tolist() == [10 * r + 1 for r in range(world)]
     ok = ok and torch.equal(extras.sum(0), torch.full((5,), float(sum(range(1, world + 1)))))
     q.put((rank, bool(ok)))
     dist.destroy_process_group()
 
 
-# even split, ragged split (5 + 4 rows), three ranks with a ragged tail (4 + 3 + 3 rows)
-@pytest.mark.parametrize("world,hw", [(2, (10, 7)), (2, (9, 5)), (3, (10, 4))])
+# even split (2 x 2 groups), partial last group (rows 16-17), an odd group count, three ranks with a ragged tail
+@pytest.mark.parametrize("world,hw", [(2, (16, 7)), (2, (18, 5)), (2, (21, 3)), (3, (30, 4))])
 def test_band_gather_multi_process(world, hw):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
@@ -65,6 +72,20 @@ def test_band_gather_multi_process(world, hw):
 def test_band_single_process():
     H, W = 6, 4
     full = _full_image(H, W)
-    outs, extras = par.gather_bands(full, (H, W), 0, 1, extra=torch.ones(3))
-    assert all(torch.equal(a.float(), b.float()) for a, b in zip(outs, full))
-    assert extras.shape == (1, 3)
+    outs, stats, extras = par.gather_bands(full, (H, W), 0, 1, extra=torch.ones(3))
+    assert all(torch.equal(a, b) for a, b in zip(outs, full))
+    assert extras.shape == (1, 3) and stats.shape == (1, 4)
+
+
+def test_band_rows_match_renderer_row_mapping():
+    """parallel.band's (row0, row_step, n_rows, row_group) means: local row l is image row
+    row0 + (l // g) * row_step + l % g -- the mapping csrc/march.cu (global_row) and SDFRenderer._image_rows apply."""
+    for H in (16, 18, 21, 30, 512, 37):
+        for world in (1, 2, 3, 8):
+            seen = []
+            for rank in range(world):
+                row0, step, n_rows, g = par.band(H, rank, world)
+                rows = [row0 + (l // g) * step + l % g for l in range(n_rows)]
+                assert rows == _band_rows(H, rank, world)
+                seen += rows
+            assert sorted(seen) == list(range(H))
