@@ -44,12 +44,13 @@ class March(C.Structure):
                 ("first_query_check", C.c_int32), ("ratio", C.c_float), ("threshold", C.c_float),
                 ("clamp_dist", C.c_float), ("replay_grad_rounding", C.c_int32), ("coarse_steps", C.c_int32 * 2),
                 ("screen", C.c_int32), ("screen_margin", C.c_float), ("screen_tpred", C.c_float),
+                ("screen_ext_margin", C.c_float),
                 ("cam_grad_levels", C.c_int32)]
 
 
 WS_FIELDS = ["ray", "entry", "exit_", "dist", "z", "flags", "nreal", "top_sdf", "top_pt", "top_zafter", "top_zgen",
              "list_a", "list_b", "pts", "sdf", "counts", "sdf_origin", "entry0", "top_lvl", "pyr_f", "pyr_i", "pyr_b",
-             "tile_mode", "seg_approx", "rq_idx", "rq_pts", "rq_sdf", "rq_cnt", "tile_counters", "view_stat"]
+             "seg_approx", "sprev", "rq_idx", "rq_pts", "rq_sdf", "rq_cnt", "tile_counters", "view_stat"]
 
 
 class Workspace(C.Structure):
@@ -67,7 +68,7 @@ PROTOTYPES = {
     "dist_fold_latent": (C.c_int, [C.POINTER(Net), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dist_decoder_forward": (C.c_int, [C.POINTER(Net), C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_float,
                                        C.c_void_p, C.c_void_p]),
-    "dist_decoder_forward_tiers": (C.c_int, [C.POINTER(Net), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_float,
+    "dist_decoder_forward_tiers": (C.c_int, [C.POINTER(Net), C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_float,
                                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dist_decoder_input_grad": (C.c_int, [C.POINTER(Net), C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_float,
                                           C.c_void_p, C.c_void_p, C.c_void_p]),

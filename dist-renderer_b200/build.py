@@ -9,7 +9,8 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdist_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"] + \
+    os.environ.get("DIST_EXTRA_NVCC_FLAGS", "").split()      # e.g. -DDIST_TC_TIMELINE for the per-layer timeline of mlp_tc.cu
 # march.cu mirrors PyTorch's separately-rounded elementwise ops: no FMA contraction there
 SOURCES = {"abi.cu": [], "march.cu": ["-fmad=false"], "mlp_simt.cu": ["-Xptxas", "-v"], "mlp_tc.cu": ["-Xptxas", "-v"]}
 

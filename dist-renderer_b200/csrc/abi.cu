@@ -45,7 +45,25 @@ int mlp_launch(const dist_net_t* net, const NetDev& nd, int engine, int mode, co
     }
     DIST_CHECK_CUDA(cudaEventRecord(g_prof_pool[g_prof_used], stream));
   }
-  const int rc = (engine == DIST_ENGINE_TC) ? mlp_tc_launch(net, nd, mode, a, stream) : mlp_simt_launch(nd, mode, a, stream);
+  int rc;
+  if (engine == DIST_ENGINE_TC) {
+    rc = mlp_tc_launch(net, nd, mode, a, stream);
+  } else {
+    // the fp32 engine knows one row range: a second segment is a second launch on the shifted arrays
+    MlpArgs a1 = a;
+    a1.n2_host = 0; a1.n2_dev = nullptr; a1.seg2_offset = 0; a1.screen_seg1 = 0; a1.seg_approx = nullptr;
+    rc = mlp_simt_launch(nd, mode, a1, stream);
+    if (rc == DIST_OK && (a.n2_dev || a.n2_host > 0)) {
+      MlpArgs a2 = a1;
+      const int64_t o = a.seg2_offset;
+      a2.points = a.points + 3 * o; a2.n_host = a.n2_host; a2.n_dev = a.n2_dev;
+      if (a.sdf) a2.sdf = a.sdf + o;
+      if (a.grad) a2.grad = a.grad + 3 * o;
+      if (a.coef) a2.coef = a.coef + o;
+      if (a.use_clamp) a2.use_clamp = a.use_clamp + o;
+      rc = mlp_simt_launch(nd, mode, a2, stream);
+    }
+  }
   if (timed) {
     DIST_CHECK_CUDA(cudaEventRecord(g_prof_pool[g_prof_used + 1], stream));
     g_prof_used += 2;
@@ -165,16 +183,16 @@ int dist_decoder_forward(const dist_net_t* net, int engine, const float* points,
   return mlp_launch(net, nd, engine, 0, a, (cudaStream_t)stream);
 }
 
-int dist_decoder_forward_tiers(const dist_net_t* net, const float* points, int64_t n_host, const int32_t* n_dev,
-                               const uint8_t* tile_mode, float screen_thresh, float* sdf, uint8_t* seg_approx,
+int dist_decoder_forward_tiers(const dist_net_t* net, const float* points, int64_t n_screen, int64_t n_exact,
+                               int64_t exact_offset, float screen_thresh, float* sdf, uint8_t* seg_approx,
                                unsigned long long* tile_counters, void* stream) {
   NetDev nd;
   int rc = make_netdev(net, &nd);
   if (rc) return rc;
-  DIST_REQUIRE(tile_mode && seg_approx, "decoder_forward_tiers: tile_mode and seg_approx are required");
+  DIST_REQUIRE(seg_approx, "decoder_forward_tiers: seg_approx is required");
   MlpArgs a{};
-  a.points = points; a.n_host = n_host; a.n_dev = n_dev; a.clamp_dist = 0.f; a.sdf = sdf;
-  a.tile_mode = tile_mode; a.screen_thresh = screen_thresh; a.seg_approx = seg_approx; a.tile_counters = tile_counters;
+  a.points = points; a.n_host = n_screen; a.n2_host = n_exact; a.seg2_offset = exact_offset; a.clamp_dist = 0.f; a.sdf = sdf;
+  a.screen_seg1 = 1; a.screen_thresh = screen_thresh; a.seg_approx = seg_approx; a.tile_counters = tile_counters;
   return mlp_launch(net, nd, DIST_ENGINE_TC, 0, a, (cudaStream_t)stream);
 }
 

@@ -53,11 +53,15 @@ struct MlpArgs {
   float* acc0;              // [N0] or null
   float* accl;              // [Nl] or null
   int64_t* rows_evaluated;  // optional counter (+= n)
-  // two-tier precision of forward launches on the tensor-core engine (mlp_tc.cu); all null / 0: full precision everywhere
-  const uint8_t* tile_mode; // [ceil(n/128)] 0 = evaluate the 128-row tile with one fp16 pass first, != 0 = three passes
+  // optional second row segment: rows [seg2_offset, seg2_offset + n2) of the same arrays (n2 from *n2_dev when set, else
+  // n2_host, which is then the capacity); seg2_offset is a multiple of 128 and >= the capacity of the first segment
+  int64_t n2_host;
+  const int32_t* n2_dev;
+  int64_t seg2_offset;
+  // two-tier precision of forward launches on the tensor-core engine (mlp_tc.cu); 0 / null: full precision everywhere
+  int screen_seg1;          // tiles of the first segment are evaluated with one fp16 pass first, the second with three
   float screen_thresh;      // one-pass values stand where every row of the 64-row half-tile has |sdf| > screen_thresh
-  int exact_last;           // never screen the tile that holds the last row
-  uint8_t* seg_approx;      // [ceil(n/64)] out: 1 = this half-tile's sdf are one-pass values
+  uint8_t* seg_approx;      // [rows / 64] out: 1 = this half-tile's sdf are one-pass values
   unsigned long long* tile_counters;  // optional [2]: tile programs evaluated with one / with three passes
 };
 int mlp_simt_launch(const NetDev& net, int mode, const MlpArgs& a, cudaStream_t stream);

@@ -39,6 +39,12 @@ __device__ __forceinline__ void load_view_pos(const Cam& cam, int v, float (&c)[
 #pragma unroll
   for (int i = 0; i < 3; ++i) c[i] = cam.c[3 * v + i];
 }
+// Row layout of the march's query arrays (ws.pts, ws.sdf, ws.list_a/b, ws.seg_approx): two segments of capacity
+// SEG = round_up(P + 1, 128) each.  Segment 1 = rows [0, n1): rays predicted far from the surface, evaluated with one fp16
+// pass first when dist_march_t.screen is on; segment 2 = rows [SEG, SEG + n2): everything else (and the origin query of step
+// 0), always at full precision.  counts[2 s] / counts[2 s + 1] hold n1 / n2 of step s.
+__host__ __device__ inline int seg_capacity(int P) { return (P + 1 + 127) / 128 * 128; }
+
 // one atomic per (warp, view) instead of one per thread; every lane of the warp must call it (v < 0: nothing to add)
 __device__ __forceinline__ void view_atomic_add(int32_t* view_stat, int slot, int v) {
   const unsigned peers = __match_any_sync(0xffffffffu, v);
@@ -177,6 +183,7 @@ __global__ void k_setup(Cam cam, dist_march_t mp, dist_workspace_t ws, float* Zd
     ws.exit_[lp] = ex; ws.dist[lp] = dist; ws.z[lp] = 0.f;
     ws.flags[lp] = hit ? 1 : 0;
     ws.nreal[lp] = 0;
+    if (ws.sprev) ws.sprev[lp] = 0.f;
     for (int b = 0; b < mp.buffer_size; ++b) {
       ws.top_sdf[(size_t)b * P + lp] = 1.0f;  // filler entries: sdf 1, point 0 (renderer.py:539-540,555)
       ws.top_zafter[(size_t)b * P + lp] = 0.f;
@@ -327,35 +334,33 @@ __global__ void k_pyr_step(Cam cam, dist_march_t mp, Level L, int step, float* p
   }
 }
 
-// appends the origin as one extra query row of step 0; counts[S+1] = counts[0] + 1 is the row count of that launch
-__global__ void k_append_origin(dist_workspace_t ws, int slot_total) {
-  const int n = ws.counts[0];
-  ws.pts[(size_t)n * 3] = 0.f; ws.pts[(size_t)n * 3 + 1] = 0.f; ws.pts[(size_t)n * 3 + 2] = 0.f;
-  ws.counts[slot_total] = n + 1;
+// the origin (filler samples, renderer.py:539-540) is the only row of segment 2 at step 0: always at full precision
+__global__ void k_append_origin(dist_workspace_t ws, int SEG) {
+  ws.pts[(size_t)SEG * 3] = 0.f; ws.pts[(size_t)SEG * 3 + 1] = 0.f; ws.pts[(size_t)SEG * 3 + 2] = 0.f;
+  ws.counts[1] = 1;
 }
 
 // ---------------------------------------------------------------------------------------------- one march step
-// two-tier precision bookkeeping (dist_march_t.screen): `tiles` = capacity of one hint array (ws.tile_mode is [3][tiles])
-__global__ void k_march_update(Cam cam, dist_march_t mp, dist_workspace_t ws, int step, int P, int tiles) {
-  const int n = ws.counts[step];
+__global__ void k_march_update(Cam cam, dist_march_t mp, dist_workspace_t ws, int step, int P) {
+  const int SEG = seg_capacity(P);
+  const int n1 = ws.counts[2 * step];
+  const int n2 = (step == 0) ? 0 : ws.counts[2 * step + 1];      // (step 0: segment 2 holds the origin query only)
+  const int n = n1 + n2;
   const bool scr = ws.seg_approx != nullptr;
-  uint8_t* hint_next = scr ? ws.tile_mode + (size_t)((step + 1) % 3) * tiles : nullptr;   // read by the next decoder launch
-  if (scr) {   // the array after next is free: clear it for the update kernel of the next step
-    uint8_t* clr = ws.tile_mode + (size_t)((step + 2) % 3) * tiles;
-    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < tiles; j += gridDim.x * blockDim.x) clr[j] = 0;
-  }
   const int32_t* cur = (step & 1) ? ws.list_b : ws.list_a;
   int32_t* nxt = (step & 1) ? ws.list_a : ws.list_b;
-  const float* pts_cur = ws.pts + (size_t)(step & 1) * (size_t)(P + 1) * 3;       // points of this step
-  float* pts_nxt = ws.pts + (size_t)((step + 1) & 1) * (size_t)(P + 1) * 3;       // points of the next step
-  if (step == 0 && blockIdx.x == 0 && threadIdx.x == 0) ws.sdf_origin[0] = ws.sdf[n];
+  const float* pts_cur = ws.pts + (size_t)(step & 1) * (size_t)(2 * SEG) * 3;       // points of this step
+  float* pts_nxt = ws.pts + (size_t)((step + 1) & 1) * (size_t)(2 * SEG) * 3;       // points of the next step
+  if (step == 0 && blockIdx.x == 0 && threadIdx.x == 0) ws.sdf_origin[0] = ws.sdf[SEG];
   const int B = mp.buffer_size;
+  const float far_thresh = mp.clamp_dist + mp.screen_margin;
   for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
-    const int i = base + threadIdx.x;
-    bool live = false, approx = false, near_pred = false;
+    const int j = base + threadIdx.x;
+    bool live = false, approx = false, pred_far = false;
     int lp = 0, v = -1;
     float znew = 0.f, entry = 0.f;
-    if (i < n) {
+    if (j < n) {
+      const int i = (j < n1) ? j : SEG + (j - n1);
       lp = cur[i];
       v = lp / cam.Pv;
       const float sdf = ws.sdf[i];
@@ -368,7 +373,15 @@ __global__ void k_march_update(Cam cam, dist_march_t mp, dist_workspace_t ws, in
       if (step == 0 && sdf > mp.threshold) ws.flags[lp] |= 2;  // renderer.py:581
       const float asdf = fabsf(sdf);
       approx = scr && ws.seg_approx[i >> 6] != 0;   // one-pass value: |sdf| > clamp + margin is all that is known exactly
-      near_pred = !(asdf > mp.screen_tpred);
+      if (scr) {
+        // Will the next sample of this ray be beyond the clamp band again?  Yes if this one is far beyond it (the march
+        // moves by ratio * clamp per step), or if the linear extrapolation of the last two samples stays beyond it with a
+        // safety margin.  A wrong "yes" costs a re-evaluation of one tile, never a wrong value.
+        const float ext = sdf + (sdf - ws.sprev[lp]);
+        pred_far = asdf > mp.screen_tpred ||
+                   (step >= 1 && asdf > far_thresh && fabsf(ext) > far_thresh + mp.screen_ext_margin && (ext > 0.f) == (sdf > 0.f));
+        ws.sprev[lp] = sdf;
+      }
       // a tanh output is in [-1, 1]: anything else is an overflow of the engine's operands (fp16 range of the tensor-core
       // engine) -- flagged per view, raised by the host when it reads view_stat back
       if (!(asdf <= 1.0f)) atomicOr(ws.view_stat + VS_STRIDE * v + VS_NONFINITE, 1);
@@ -381,15 +394,17 @@ __global__ void k_march_update(Cam cam, dist_march_t mp, dist_workspace_t ws, in
       }
     }
     view_atomic_max(ws.view_stat, VS_STEPS, v, step + 1);   // view v executed this step
-    const int idx = warp_append(ws.counts + step + 1, live);
+    // compaction into the next step's two segments (without screening everything goes to segment 1)
+    const bool to1 = live && (!scr || pred_far), to2 = live && !to1;
+    int idx = warp_append(ws.counts + 2 * (step + 1), to1);
+    const int idx2 = warp_append(ws.counts + 2 * (step + 1) + 1, to2);
+    if (idx2 >= 0) idx = SEG + idx2;
     if (idx >= 0) {
       float ray[3] = {ws.ray[lp], ws.ray[P + lp], ws.ray[2 * P + lp]}, p[3], c[3];
       load_view_pos(cam, v, c);
       point_on_ray(cam, c, ray, entry + znew, p);
       nxt[idx] = lp;
       pts_nxt[(size_t)idx * 3] = p[0]; pts_nxt[(size_t)idx * 3 + 1] = p[1]; pts_nxt[(size_t)idx * 3 + 2] = p[2];
-      // a row this close to the band may be inside it after the next step: its tile skips the one-pass attempt
-      if (scr && near_pred) hint_next[idx >> 7] = 1;
     }
   }
 }
@@ -677,16 +692,16 @@ int render_depth_fwd(const dist_net_t* net, int engine, const dist_camera_t* cam
   const int tb = 256, gb = (P + tb - 1) / tb;
   // two-tier precision of the march rows (tensor-core engine only)
   const bool scr = mp->screen != 0 && engine == DIST_ENGINE_TC;
-  const int tiles = (P + 1 + 127) / 128;
+  const int SEG = seg_capacity(P);
   dist_workspace_t wsv = *ws;
   if (scr) {
-    DIST_REQUIRE(ws->tile_mode && ws->seg_approx && ws->rq_idx && ws->rq_pts && ws->rq_sdf && ws->rq_cnt,
+    DIST_REQUIRE(ws->seg_approx && ws->sprev && ws->rq_idx && ws->rq_pts && ws->rq_sdf && ws->rq_cnt,
                  "workspace: two-tier precision buffers missing");
-    DIST_REQUIRE(mp->screen_margin > 0.f && mp->screen_tpred >= mp->clamp_dist, "two-tier precision: bad margin / prediction threshold");
-    DIST_CHECK_CUDA(cudaMemsetAsync(ws->tile_mode, 0, 3 * (size_t)tiles, st));
+    DIST_REQUIRE(mp->screen_margin > 0.f && mp->screen_tpred >= mp->clamp_dist && mp->screen_ext_margin >= 0.f,
+                 "two-tier precision: bad margin / prediction thresholds");
     DIST_CHECK_CUDA(cudaMemsetAsync(ws->rq_cnt, 0, sizeof(int32_t), st));
   } else {
-    wsv.tile_mode = nullptr; wsv.seg_approx = nullptr;     // the kernels key on seg_approx
+    wsv.seg_approx = nullptr;     // the kernels key on seg_approx
   }
   ws = &wsv;
   Level L1, L2;
@@ -725,26 +740,24 @@ int render_depth_fwd(const dist_net_t* net, int engine, const dist_camera_t* cam
     }
   }
   const int S = mp->march_step;
-  DIST_CHECK_CUDA(cudaMemsetAsync(ws->counts, 0, sizeof(int32_t) * (S_total + 2), st));
+  DIST_CHECK_CUDA(cudaMemsetAsync(ws->counts, 0, sizeof(int32_t) * 2 * (S_total + 2), st));
   k_setup<<<(cam.n_views * setup_threads_per_view(cam.W, cam.n_rows) + tb - 1) / tb, tb, 0, st>>>(cam, *mp, *ws, Zdepth, mask, min_sdf, P,
                                                                                                 L1, L2); count_launch();
-  k_append_origin<<<1, 1, 0, st>>>(*ws, S + 1); count_launch();
+  k_append_origin<<<1, 1, 0, st>>>(*ws, SEG); count_launch();
   DIST_CHECK_CUDA(cudaGetLastError());
   const int gu = min(gb, 4 * num_sms());
   for (int s = 0; s < S; ++s) {
     MlpArgs a{};
-    a.points = ws->pts + (size_t)(s & 1) * (size_t)(P + 1) * 3; a.n_host = P + (s == 0 ? 1 : 0);
-    a.n_dev = ws->counts + (s == 0 ? S + 1 : s);
+    // segment 1 (rays predicted far from the surface; one-pass tiles when screening) + segment 2 (the rest, full precision)
+    a.points = ws->pts + (size_t)(s & 1) * (size_t)(2 * SEG) * 3;
+    a.n_host = P; a.n_dev = ws->counts + 2 * s;
+    a.n2_host = P + 1; a.n2_dev = ws->counts + 2 * s + 1; a.seg2_offset = SEG;
     a.clamp_dist = 0.f; a.sdf = ws->sdf; a.rows_evaluated = rows_eval;
     a.tile_counters = ws->tile_counters;
-    if (scr) {
-      a.tile_mode = ws->tile_mode + (size_t)(s % 3) * tiles; a.screen_thresh = mp->clamp_dist + mp->screen_margin;
-      a.exact_last = (s == 0) ? 1 : 0;      // the origin query of step 0 (filler samples, renderer.py:539-540) is exact
-      a.seg_approx = ws->seg_approx;
-    }
+    if (scr) { a.screen_seg1 = 1; a.screen_thresh = mp->clamp_dist + mp->screen_margin; a.seg_approx = ws->seg_approx; }
     rc = mlp_launch(net, nd, engine, 0, a, st);
     if (rc) return rc;
-    k_march_update<<<gu, tb, 0, st>>>(cam, *mp, *ws, s, P, tiles); count_launch();
+    k_march_update<<<gu, tb, 0, st>>>(cam, *mp, *ws, s, P); count_launch();
   }
   if (scr) {
     k_requery_gen<<<gb, tb, 0, st>>>(*mp, *ws, P); count_launch();

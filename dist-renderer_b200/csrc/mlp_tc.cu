@@ -35,6 +35,16 @@
 namespace dist {
 namespace {
 
+// -DDIST_TC_TIMELINE: the MMA issuer of cluster 0 also accumulates, for its second tile, the cycles it spends waiting for
+// activation blocks (A_FULL) and for weight stages (W_FULL) per layer: dbg_out[256 + 2 m], dbg_out[257 + 2 m]
+#ifdef DIST_TC_TIMELINE
+#define TL_BEGIN() const long long tl_c0 = clock64()
+#define TL_END(slot_) do { if (io.dbg_out && cluster_id == 0 && i == 1 && lane == 0) io.dbg_out[256 + 2 * m + (slot_)] += clock64() - tl_c0; } while (0)
+#else
+#define TL_BEGIN() do {} while (0)
+#define TL_END(slot_) do {} while (0)
+#endif
+
 constexpr int NST = 6;                 // weight ring stages
 constexpr int STAGE_BYTES = 16384;     // per CTA: [hi 8 KB][lo 8 KB]
 constexpr int OFF_AHI = 0, OFF_ALO = 65536, OFF_W = 131072;
@@ -78,14 +88,15 @@ struct TcParams {
 
 struct TcIO {
   const float* points; int64_t n_host; const int32_t* n_dev; float clamp_dist;
+  int64_t n2_host; const int32_t* n2_dev; int64_t seg2_offset;   // optional second row segment [seg2_offset, seg2_offset + n2)
   float* sdf; float* grad; const float* coef; const uint8_t* use_clamp; float* acc0; float* accl;
   int64_t* rows_evaluated;
   long long* dbg_out;   // DIST_TC_DEBUG bit2: [cycles, ns] of CTA 0
-  // two-tier precision (MODE 0 only; see the kernel comment).  tile_mode == nullptr: every tile at full precision.
-  const uint8_t* tile_mode;     // [tiles] 0: try ONE fp16 pass first ("screen"), != 0: three split-precision passes directly
+  // two-tier precision (MODE 0 only; see the kernel comment).  screen_seg1 == 0: every tile at full precision.
+  int screen_seg1;              // tiles of the first row segment try ONE fp16 pass first ("screen"); the second segment
+                                // always gets the three split-precision passes
   float screen_thresh;          // a screened half-tile passes when all its rows have |sdf| > screen_thresh
-  int exact_last;               // the tile that holds the last row (the march's origin query) is never screened
-  uint8_t* seg_approx;          // [ceil(n/64)] out: 1 = the sdf of this 64-row half-tile are one-pass values
+  uint8_t* seg_approx;          // [rows / 64] out: 1 = the sdf of this 64-row half-tile are one-pass values
   unsigned long long* tile_counters;   // optional [2]: += tiles evaluated with one pass / with three passes
 };
 
@@ -194,12 +205,17 @@ template <int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
 mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_hi, const TcParams P, const TcIO io) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  const int64_t n = io.n_dev ? (int64_t)*io.n_dev : io.n_host;
+  // rows: segment 1 = [0, n1), segment 2 = [seg2_offset, seg2_offset + n2) (seg2_offset a multiple of 128)
+  const int64_t n1 = io.n_dev ? (int64_t)*io.n_dev : io.n_host;
+  const int64_t n2 = io.n2_dev ? (int64_t)*io.n2_dev : io.n2_host;
+  const int64_t n = n1 + n2;
   if (n <= 0) return;
   const uint32_t rank = cluster_ctarank();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
-  const int64_t n_tiles = (n + 127) / 128;
+  const int64_t tiles1 = (n1 + 127) / 128, n_tiles = tiles1 + (n2 + 127) / 128;
+  auto row0_of = [&](int64_t t) -> int64_t { return (t < tiles1) ? t * 128 : io.seg2_offset + (t - tiles1) * 128; };
+  auto lim_of = [&](int64_t t) -> int64_t { return (t < tiles1) ? n1 : io.seg2_offset + n2; };
   if (blockIdx.x == 0 && tid == 0 && io.rows_evaluated)
     atomicAdd(reinterpret_cast<unsigned long long*>(io.rows_evaluated), (unsigned long long)n);
 
@@ -216,21 +232,19 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 8 * (2 * NST + 37));
   const int n_prog = P.n_prog;
 
-  // ---- two-tier precision (MODE 0 with io.tile_mode): a tile whose mode byte is 0 is first evaluated with ONE fp16 pass
+  // ---- two-tier precision (MODE 0 with io.screen_seg1): a tile of the first row segment is first evaluated with ONE fp16 pass
   // (A_hi W_hi; only the hi halves of the weight stages are fetched).  If all 64 rows of a CTA come out with
   // |sdf| > screen_thresh (safely beyond the march's clamp, so the step they cause does not depend on their last bits)
   // the half-tile is done and flagged in io.seg_approx; if either CTA of the pair sees a nearer row the tile is recorded
   // in that CTA's fail bitmap and re-evaluated at full precision in a second pass over this cluster's tiles ("phase 1")
   // after a cluster barrier -- no other communication between roles or CTAs is needed, every role walks the same lists.
   const int cnt = (cluster_id < n_tiles) ? (int)((n_tiles - cluster_id + n_clusters - 1) / n_clusters) : 0;  // tiles of this cluster
-  const bool screening = (MODE == 0) && io.tile_mode != nullptr && cnt <= 32 * FAIL_WORDS;
+  const bool screening = (MODE == 0) && io.screen_seg1 != 0 && cnt <= 32 * FAIL_WORDS;
   volatile uint32_t* near_flag = reinterpret_cast<volatile uint32_t*>(smem + OFF_FAIL);
   volatile uint32_t* fail_words = reinterpret_cast<volatile uint32_t*>(smem + OFF_FAIL + 16);
   const uint32_t fail_addr = sbase + OFF_FAIL + 16;
   auto tile_of = [&](int i) -> int64_t { return cluster_id + (int64_t)i * n_clusters; };
-  auto tile_exact = [&](int64_t t) -> bool {
-    return !screening || io.tile_mode[t] != 0 || (io.exact_last && t == n_tiles - 1);
-  };
+  auto tile_exact = [&](int64_t t) -> bool { return !screening || t >= tiles1; };
   // next tile index of this cluster after i (i = -1: the first), -1 when exhausted.  phase 0: all tiles; phase 1: tiles
   // whose fail bit is set in this CTA's or the peer's bitmap (read through distributed shared memory)
   auto next_tile = [&](int phase, int i) -> int {
@@ -274,22 +288,36 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
       for (int phase = 0; phase < 2; ++phase) {
         for (int i = next_tile(phase, -1); i >= 0; i = next_tile(phase, i)) {
           const bool exact = (phase == 1) || tile_exact(tile_of(i));
-          const CUtensorMap* tm = exact ? &tmap : &tmap_hi;          // one-pass tiles fetch [hi 8 KB] of each stage only
-          const uint32_t bytes = exact ? 2 * STAGE_BYTES : STAGE_BYTES;
           for (int m = 0; m < n_prog; ++m) {
-            const int nstage = P.L[m].kc32 * P.L[m].nh, sb = P.L[m].stage_base;
-            for (int s = 0; s < nstage; ++s) {
+            const int kc32 = P.L[m].kc32, sb = P.L[m].stage_base;
+            // full precision: one ring slot = one 32-wide K chunk, [hi 8 KB][lo 8 KB] per CTA.
+            // one pass: one ring slot = the hi halves of TWO consecutive K chunks (the same bytes in flight per slot: the ring
+            // of NST slots covers the L2 -> smem round trip only with 16 KB per slot; 8 KB slots ran at a third of the MMA rate)
+            const int nslot = exact ? kc32 * P.L[m].nh : (kc32 / 2) * P.L[m].nh;
+            for (int s = 0; s < nslot; ++s) {
               const uint32_t slot = p_slot, ph = p_phase;
               if (++p_slot == NST) { p_slot = 0; p_phase ^= 1; }
               mbar_wait(W_EMPTY(slot), ph ^ 1);
               if (elect_one()) {
-                if (rank == 0) mbar_expect_tx(W_FULL(slot), bytes);
-                const int row = ((sb + s) * 2 + (int)rank) * (STAGE_BYTES / 128);
-                asm volatile(
-                    "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
-                        "r"(sbase + OFF_W + slot * STAGE_BYTES),
-                    "l"(tm), "r"(W_FULL(slot) & bar_leader_mask), "r"(0), "r"(row)
-                    : "memory");
+                if (rank == 0) mbar_expect_tx(W_FULL(slot), 2 * STAGE_BYTES);
+                const uint32_t dst = sbase + OFF_W + slot * STAGE_BYTES;
+                const uint32_t bar = W_FULL(slot) & bar_leader_mask;
+                if (exact) {
+                  const int row = ((sb + s) * 2 + (int)rank) * (STAGE_BYTES / 128);
+                  asm volatile(
+                      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
+                          "r"(dst), "l"(&tmap), "r"(bar), "r"(0), "r"(row)
+                      : "memory");
+                } else {
+#pragma unroll
+                  for (int c = 0; c < 2; ++c) {
+                    const int row = ((sb + 2 * s + c) * 2 + (int)rank) * (STAGE_BYTES / 128);
+                    asm volatile(
+                        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
+                            "r"(dst + c * (STAGE_BYTES / 2)), "l"(&tmap_hi), "r"(bar), "r"(0), "r"(row)
+                        : "memory");
+                  }
+                }
               }
               __syncwarp();
             }
@@ -329,11 +357,58 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
           for (int h = 0; h < nh; ++h) {
             const uint32_t d_addr = tmem + buf * 256 + h * 128;
             const bool last_pass = (h == nh - 1);
+            if (!exact) {
+              // one pass: a ring slot holds the hi halves of two K chunks -> 4 MMAs per slot, two slots per round trip
+              for (int kc = 0; kc < kc32; kc += 4) {
+                const int nsl = (kc + 2 < kc32) ? 2 : 1;
+                if (h == 0) {
+                  TL_BEGIN();
+                  for (int c = 0; c < 2 * nsl; ++c) mbar_wait_cluster(A_FULL(kc + c), (a_phase >> (kc + c)) & 1);
+                  a_phase ^= (nsl == 2 ? 15u : 3u) << kc;
+                  TL_END(0);
+                }
+                const uint32_t slot0 = w_slot, ph0 = w_phase;
+                uint32_t slot1 = slot0, ph1 = ph0;
+                if (++w_slot == NST) { w_slot = 0; w_phase ^= 1; }
+                if (nsl == 2) {
+                  slot1 = w_slot; ph1 = w_phase;
+                  if (++w_slot == NST) { w_slot = 0; w_phase ^= 1; }
+                }
+                {
+                  TL_BEGIN();
+                  mbar_wait(W_FULL(slot0), ph0);
+                  if (nsl == 2) mbar_wait(W_FULL(slot1), ph1);
+                  TL_END(1);
+                }
+                tc_fence_after();
+                if (elect_one()) {
+                  for (int u = 0; u < nsl; ++u) {
+                    const uint32_t slot = u ? slot1 : slot0;
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+#pragma unroll
+                      for (int ks = 0; ks < 2; ++ks) {
+                        const int kk = kc + 2 * u + c;
+                        const uint64_t a_off = (uint64_t)((kk * 4 + ks * 2) * 64);
+                        const uint64_t b_off = (uint64_t)(slot * (STAGE_BYTES / 16) + c * 512 + ks * 256);
+                        mma_f16_2cta(d_addr, a_hi0 + a_off, b_0 + b_off, idesc, (kk | ks) ? 1u : 0u);
+                      }
+                    }
+                    commit_mc(W_EMPTY(slot));
+                    if (last_pass) { commit_mc(A_FREE(kc + 2 * u)); commit_mc(A_FREE(kc + 2 * u + 1)); }
+                  }
+                  if (kc + 4 >= kc32) commit_mc(D_FULL(buf, h));
+                }
+                __syncwarp();
+              }
+            } else
             for (int kc = 0; kc < kc32; kc += 2) {
               if (h == 0) {
+                TL_BEGIN();
                 mbar_wait_cluster(A_FULL(kc), (a_phase >> kc) & 1);
                 mbar_wait_cluster(A_FULL(kc + 1), (a_phase >> (kc + 1)) & 1);
                 a_phase ^= (3u << kc);
+                TL_END(0);
 #ifdef DIST_TC_TIMELINE
                 if (io.dbg_out && cluster_id == 0 && t == cluster_id + n_clusters && lane == 0 && kc == 0) io.dbg_out[8 + m * 4 + 0] = clock64();
 #endif
@@ -343,8 +418,12 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
               if (slot1 == NST) { slot1 = 0; ph1 ^= 1; }
               w_slot = slot1 + 1; w_phase = ph1;
               if (w_slot == NST) { w_slot = 0; w_phase ^= 1; }
-              mbar_wait(W_FULL(slot0), ph0);
-              mbar_wait(W_FULL(slot1), ph1);
+              {
+                TL_BEGIN();
+                mbar_wait(W_FULL(slot0), ph0);
+                mbar_wait(W_FULL(slot1), ph1);
+                TL_END(1);
+              }
               tc_fence_after();
               if (elect_one()) {
 #pragma unroll
@@ -355,10 +434,8 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
                     const uint64_t a_off = (uint64_t)(((kc + u) * 4 + ks * 2) * 64);
                     const uint64_t b_off = (uint64_t)(slot * (STAGE_BYTES / 16) + ks * 256);
                     mma_f16_2cta(d_addr, a_hi0 + a_off, b_0 + b_off, idesc, ((kc + u) | ks) ? 1u : 0u);
-                    if (exact) {
-                      mma_f16_2cta(d_addr, a_lo0 + a_off, b_0 + b_off, idesc, 1u);
-                      mma_f16_2cta(d_addr, a_hi0 + a_off, b_0 + b_off + 512, idesc, 1u);
-                    }
+                    mma_f16_2cta(d_addr, a_lo0 + a_off, b_0 + b_off, idesc, 1u);
+                    mma_f16_2cta(d_addr, a_hi0 + a_off, b_0 + b_off + 512, idesc, 1u);
                   }
                   commit_mc(W_EMPTY(slot));
                   if (last_pass) commit_mc(A_FREE(kc + u));
@@ -404,8 +481,8 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
     float acc0r[2] = {0.f, 0.f}, acclr[2] = {0.f, 0.f};  // MODE 2: per-lane running column sums
 
     auto load_point = [&](int64_t t) {
-      const int64_t gr = t * 128 + rank * 64 + row;
-      if (gr < n) { px = io.points[gr * 3]; py = io.points[gr * 3 + 1]; pz = io.points[gr * 3 + 2]; }
+      const int64_t gr = row0_of(t) + rank * 64 + row;
+      if (gr < lim_of(t)) { px = io.points[gr * 3]; py = io.points[gr * 3 + 1]; pz = io.points[gr * 3 + 2]; }
       else { px = py = pz = 0.f; }
     };
     auto signal_block = [&](int kc) {   // this warp's 32 rows x 32 features of A block kc are written
@@ -470,7 +547,8 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
       const int64_t t = tile_of(i);
       const int inext = next_tile(phase, i);
       const bool exact = (phase == 1) || tile_exact(t);
-      const int64_t gr = t * 128 + rank * 64 + row;
+      const int64_t gr = row0_of(t) + rank * 64 + row;
+      const bool row_ok = gr < lim_of(t);
       float dot = 0.f, rowscale = 0.f, dx = 0.f, dy = 0.f, dz = 0.f;
       uint32_t mk0s[2] = {0u, 0u};
       for (int m = 0; m < n_prog; ++m, ++G) {
@@ -641,18 +719,18 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
             if (P.use_tanh) { t1 = o; o = tanhf(o); }
             float oc = o;
             if (io.clamp_dist > 0.f) oc = fminf(fmaxf(o, -io.clamp_dist), io.clamp_dist);
-            if (gr < n && io.sdf) io.sdf[gr] = oc;
+            if (row_ok && io.sdf) io.sdf[gr] = oc;
             // one-pass tile: a row that may be inside the clamp band (or is not a number) fails the half-tile
-            if (MODE == 0 && !exact && gr < n && !(fabsf(o) > io.screen_thresh)) *near_flag = 1u;
+            if (MODE == 0 && !exact && row_ok && !(fabsf(o) > io.screen_thresh)) *near_flag = 1u;
             if (MODE != 0) {
               float d = 1.f - o * o;
               if (P.use_tanh) d *= (1.f - t1 * t1);
               bool uc = io.clamp_dist > 0.f;
-              if (MODE == 2 && io.use_clamp) uc = (gr < n) ? (io.use_clamp[gr] != 0) : false;
+              if (MODE == 2 && io.use_clamp) uc = row_ok ? (io.use_clamp[gr] != 0) : false;
               if (uc && !(o >= -io.clamp_dist && o <= io.clamp_dist)) d = 0.f;
               float cf = 1.f;
-              if (MODE == 2 && io.coef) cf = (gr < n) ? io.coef[gr] : 0.f;
-              if (gr >= n) cf = 0.f;
+              if (MODE == 2 && io.coef) cf = row_ok ? io.coef[gr] : 0.f;
+              if (!row_ok) cf = 0.f;
               rowd[row] = d * cf;
             }
           }
@@ -663,7 +741,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
               if (*near_flag) { fail_words[i >> 5] |= 1u << (i & 31); *near_flag = 0u; }   // redo in phase 1
               else approx = true;
             }
-            if (io.seg_approx && (t * 2 + rank) * 64 < n) io.seg_approx[t * 2 + rank] = approx ? 1 : 0;
+            if (io.seg_approx && row0_of(t) + rank * 64 < lim_of(t)) io.seg_approx[(row0_of(t) >> 6) + rank] = approx ? 1 : 0;
             if (exact) ++n_tiles_3pass; else ++n_tiles_1pass;
           }
           if (MODE != 0) {
@@ -704,7 +782,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
               res[k] = row_sum8();
               epi_bar_sync();
             }
-            if (pslot == 0 && gr < n && io.grad) {
+            if (pslot == 0 && row_ok && io.grad) {
               const float rs = rowscale * (1.f / sD);
               io.grad[gr * 3] = res[0] * rs; io.grad[gr * 3 + 1] = res[1] * rs; io.grad[gr * 3 + 2] = res[2] * rs;
             }
@@ -766,7 +844,7 @@ int mlp_tc_launch(const dist_net_t* net, const NetDev& nd, int mode, const MlpAr
   DIST_REQUIRE(net->tc_blob && net->tc_scale, "tensor-core engine: operands not prepared (tc.prepare)");
   const int nl = nd.n_layers;
   DIST_REQUIRE(nl >= 4 && nl <= 10, "tensor-core engine: %d layers unsupported", nl);
-  if (a.n_host <= 0 && !a.n_dev) return DIST_OK;
+  if (a.n_host <= 0 && !a.n_dev && a.n2_host <= 0 && !a.n2_dev) return DIST_OK;
   EncodeFn encode = get_encode();
   if (!encode) { set_error("cuTensorMapEncodeTiled not available"); return DIST_E_UNSUPPORTED; }
 
@@ -815,13 +893,16 @@ int mlp_tc_launch(const dist_net_t* net, const NetDev& nd, int mode, const MlpAr
   io.points = a.points; io.n_host = a.n_host; io.n_dev = a.n_dev; io.clamp_dist = a.clamp_dist;
   io.sdf = a.sdf; io.grad = a.grad; io.coef = a.coef; io.use_clamp = a.use_clamp; io.acc0 = a.acc0; io.accl = a.accl;
   io.rows_evaluated = a.rows_evaluated;
-  io.tile_mode = (mode == 0) ? a.tile_mode : nullptr;
-  io.screen_thresh = a.screen_thresh; io.exact_last = a.exact_last; io.seg_approx = a.seg_approx;
+  io.n2_host = a.n2_host; io.n2_dev = a.n2_dev; io.seg2_offset = a.seg2_offset;
+  io.screen_seg1 = (mode == 0) ? a.screen_seg1 : 0;
+  io.screen_thresh = a.screen_thresh; io.seg_approx = a.seg_approx;
   io.tile_counters = a.tile_counters;
-  DIST_REQUIRE(io.tile_mode == nullptr || io.seg_approx != nullptr, "tensor-core engine: two-tier precision needs seg_approx");
+  DIST_REQUIRE(!io.screen_seg1 || io.seg_approx != nullptr, "tensor-core engine: two-tier precision needs seg_approx");
+  DIST_REQUIRE((a.n2_host == 0 && !a.n2_dev) || (a.seg2_offset % 128 == 0 && a.seg2_offset >= a.n_host),
+               "tensor-core engine: the second row segment must start at a multiple of 128 behind the first");
   io.dbg_out = nullptr;
   static long long* dbg_buf = nullptr;
-  if (P.dbg & 4) { if (!dbg_buf) { cudaMalloc(&dbg_buf, 2048); cudaMemset(dbg_buf, 0, 2048); } io.dbg_out = dbg_buf; }
+  if (P.dbg & 4) { if (!dbg_buf) { cudaMalloc(&dbg_buf, 4096); cudaMemset(dbg_buf, 0, 4096); } io.dbg_out = dbg_buf; }
 
   // tensor map over the blob: rows of 128 B; one box = one 16 KB stage of one CTA
   CUtensorMap tmap;
@@ -852,7 +933,7 @@ int mlp_tc_launch(const dist_net_t* net, const NetDev& nd, int mode, const MlpAr
     DIST_CHECK_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr_done = true;
   }
-  const int64_t tiles = (a.n_host + 127) / 128;
+  const int64_t tiles = (a.n_host + 127) / 128 + (a.n2_host + 127) / 128;   // capacities when the counts live on the device
   int clusters = num_sms() / 2;
   if (tiles < clusters) clusters = (int)tiles;
   if (clusters < 1) clusters = 1;
@@ -872,9 +953,12 @@ int mlp_tc_launch(const dist_net_t* net, const NetDev& nd, int mode, const MlpAr
       cudaMemcpy(ev, dbg_buf, 2048, cudaMemcpyDeviceToHost);
       const long long t0 = ev[8];
       fprintf(stderr, "[tc dbg] previous tile: last MMA issue at %lld (relative to this tile's first MMA)\n", ev[200] - t0);
+      long long wt[64];
+      cudaMemcpy(wt, dbg_buf + 256, sizeof(wt), cudaMemcpyDeviceToHost);
       for (int m = 0; m < P.n_prog; ++m)
-        fprintf(stderr, "[tc dbg] layer %2d: mma start %7lld  issue end %7lld | epi start %7lld  epi end %7lld\n", m, ev[8 + m * 4] - t0,
-                ev[8 + m * 4 + 1] - t0, ev[8 + m * 4 + 2] - t0, ev[8 + m * 4 + 3] - t0);
+        fprintf(stderr, "[tc dbg] layer %2d: mma start %7lld  issue end %7lld | epi start %7lld  epi end %7lld | issuer waited for A %6lld, for W %6lld\n",
+                m, ev[8 + m * 4] - t0, ev[8 + m * 4 + 1] - t0, ev[8 + m * 4 + 2] - t0, ev[8 + m * 4 + 3] - t0, wt[2 * m], wt[2 * m + 1]);
+      cudaMemset(dbg_buf + 256, 0, sizeof(wt));
     }
 #endif
   }

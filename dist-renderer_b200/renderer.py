@@ -64,7 +64,8 @@ class _RenderDepthFn(torch.autograd.Function):
         # this decoder were measured to be accurate to half the margin
         screen = plan.tc.get("screen") if (engine == _abi.ENGINE_TC and plan.tc is not None and ren.screen) else None
         if screen:
-            mp.screen, mp.screen_margin, mp.screen_tpred = 1, screen["margin"], ren.screen_tpred
+            mp.screen, mp.screen_margin = 1, screen["margin"]
+            mp.screen_tpred, mp.screen_ext_margin = ren.screen_tpred, ren.screen_ext_margin
         f32 = dict(device=dev, dtype=torch.float32)
         saved = {
             "flags": torch.empty(P, device=dev, dtype=torch.uint8), "nreal": torch.empty(P, device=dev, dtype=torch.int32),
@@ -156,7 +157,7 @@ class SDFRenderer(object):
     def __init__(self, decoder, intrinsic, img_hw=None, transform_matrix=None, march_step=50, buffer_size=5,
                  ray_marching_ratio=1.5, use_depth2normal=False, max_sample_dist=0.2, radius=1.0, threshold=5e-5,
                  scale_list=[4, 2, 1], march_step_list=[3, 3, -1], use_gpu=True, is_eval=True, engine=None,
-                 rows=None, screen=None, screen_tpred=0.28):
+                 rows=None, screen=None, screen_tpred=0.30, screen_ext_margin=0.04):
         # renderer.py:13-59
         self.decoder = decoder
         if use_gpu and torch.cuda.device_count() == 0:
@@ -215,6 +216,7 @@ class SDFRenderer(object):
         import os
         self.screen = (os.environ.get("DIST_SCREEN", "1") != "0") if screen is None else bool(screen)
         self.screen_tpred = float(os.environ.get("DIST_SCREEN_TPRED", screen_tpred))
+        self.screen_ext_margin = float(os.environ.get("DIST_SCREEN_EXT", screen_ext_margin))
         self._homo_calib = None
         self._calib_map = None
         self._scr = None
@@ -349,14 +351,15 @@ class SDFRenderer(object):
             self._scr["pyr_b"] = torch.empty(npc, device=self.device, dtype=torch.uint8)
         if self._scr is None:
             P, dev = self.P, self.device
+            SEG = (P + 1 + 127) // 128 * 128      # capacity of one row segment of the query arrays (dist_b200.h)
             f32 = dict(device=dev, dtype=torch.float32)
             i32 = dict(device=dev, dtype=torch.int32)
             self._scr = {
                 "ray": torch.empty(3, P, **f32), "entry": torch.empty(P, **f32), "exit_": torch.empty(P, **f32),
                 "entry0": torch.empty(P, **f32), "pyr_f": None, "pyr_i": None, "pyr_b": None,
-                "z": torch.empty(P, **f32), "list_a": torch.empty(P, **i32), "list_b": torch.empty(P, **i32),
-                "pts": torch.empty(2, P + 1, 3, **f32), "sdf": torch.empty(P + 1, **f32),
-                "counts": torch.empty(self.march_step + 2, **i32),
+                "z": torch.empty(P, **f32), "list_a": torch.empty(2 * SEG, **i32), "list_b": torch.empty(2 * SEG, **i32),
+                "pts": torch.empty(2, 2 * SEG, 3, **f32), "sdf": torch.empty(2 * SEG, **f32),
+                "counts": torch.empty(2 * (self.march_step + 2), **i32),
                 "view_stat": torch.zeros(self.n_views, 4, **i32),
                 "n_idx": torch.empty(P, **i32), "n_pts": torch.empty(P, 3, **f32), "n_grad": torch.empty(P, 3, **f32),
                 "n_cnt": torch.empty(1, **i32),
@@ -364,9 +367,8 @@ class SDFRenderer(object):
                 "b_row": torch.empty(P * self.buffer_size, **i32), "b_pts": torch.empty(P * self.buffer_size, 3, **f32),
                 "b_coef": torch.empty(P * self.buffer_size, **f32), "b_dpts": torch.empty(P * self.buffer_size, 3, **f32),
                 "b_cnt": torch.empty(1, **i32),
-                # two-tier precision: 3 rotating per-tile hint arrays + per-half-tile one-pass flags
-                "tile_mode": torch.zeros(3 * ((P + 1 + 127) // 128), device=dev, dtype=torch.uint8),
-                "seg_approx": torch.zeros(2 * ((P + 1 + 127) // 128), device=dev, dtype=torch.uint8),
+                # two-tier precision: per-half-tile one-pass flags, the rays' previous sdf
+                "seg_approx": torch.zeros(2 * SEG // 64, device=dev, dtype=torch.uint8), "sprev": torch.empty(P, **f32),
             }
             # the exact re-query rows of the forward pass live in the backward replay scratch (free until backward)
             self._scr.update(rq_idx=self._scr["b_row"], rq_pts=self._scr["b_pts"], rq_sdf=self._scr["b_coef"],

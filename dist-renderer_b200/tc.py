@@ -180,16 +180,14 @@ def _screen_check(plan, n_points=8192):
     pts = ((torch.rand(n_points, 3, generator=g) - 0.5) * 2.0).to(plan.device)
     lat = (0.1 * torch.randn(plan.latent_size, generator=g)).to(plan.device) if plan.latent_size > 0 else None
     b0, bl, _ = plan.fold(lat, st)
-    net = plan.c_net(b0, bl, bl * S_ACT if bl is not None else None)
+    bl_tc = bl * S_ACT if bl is not None else None      # (kept alive: the descriptor only holds its address)
+    net = plan.c_net(b0, bl, bl_tc)
     exact = torch.empty(n_points, device=plan.device)
     one = torch.empty(n_points, device=plan.device)
-    tiles = (n_points + 127) // 128
-    mode = torch.zeros(tiles, device=plan.device, dtype=torch.uint8)
-    seg = torch.zeros(2 * tiles, device=plan.device, dtype=torch.uint8)
+    seg = torch.zeros((n_points + 63) // 64, device=plan.device, dtype=torch.uint8)
     _abi.check(lib.dist_decoder_forward(net, _abi.ENGINE_TC, _abi.ptr(pts), n_points, None, 0.0, _abi.ptr(exact), st))
-    # threshold -1: no |sdf| is <= -1, so every half-tile keeps its one-pass values
-    _abi.check(lib.dist_decoder_forward_tiers(net, _abi.ptr(pts), n_points, None, _abi.ptr(mode), -1.0, _abi.ptr(one),
-                                              _abi.ptr(seg), None, st))
+    # all rows in the one-pass segment; threshold -1: no |sdf| is <= -1, so every half-tile keeps its one-pass values
+    _abi.check(lib.dist_decoder_forward_tiers(net, _abi.ptr(pts), n_points, 0, 0, -1.0, _abi.ptr(one), _abi.ptr(seg), None, st))
     err = float((one - exact).abs().max())
     ok = bool(seg.bool().all()) and err < SCREEN_MARGIN / 4
     if not ok:

@@ -118,7 +118,10 @@ typedef struct dist_march {
                                  only ever used where the reference's result does not depend on it, except a ray's
                                  smallest |sdf|, which is re-queried at full precision before the maps are written */
   float screen_margin;        /* one-pass values must be accurate to screen_margin / 2 (checked at prepare time) */
-  float screen_tpred;         /* tiles with a row whose previous |sdf| was <= screen_tpred skip the one-pass attempt */
+  float screen_tpred;         /* a ray whose last |sdf| exceeds screen_tpred is predicted "far" for its next sample ... */
+  float screen_ext_margin;    /* ... as is one whose last two samples extrapolate linearly to beyond clamp_dist +
+                                 screen_margin + screen_ext_margin; rays predicted far are compacted into the first row
+                                 segment of the next step (one-pass tiles), all others into the second (three passes) */
   int32_t cam_grad_levels;    /* dist_render_depth_bwd: which samples carry a camera gradient -- bit 0: samples of the
                                  full-resolution march, bit 1: samples inherited from the coarse pyramid levels
                                  (0 = both).  no_grad_camera detaches only the points of ray_marching_recursive
@@ -141,11 +144,11 @@ typedef struct dist_workspace {
   float* top_pt;     /* [B][3][P] their points (decoder frame) */
   float* top_zafter; /* [B][P] marching depth after the step that produced the sample */
   float* top_zgen;   /* [B][P] absolute ray depth the sample point was generated at (NaN: not on this ray) */
-  int32_t* list_a;   /* [P] active ray list (ping) */
-  int32_t* list_b;   /* [P] active ray list (pong) */
-  float* pts;        /* [2][P+1][3] query points, ping-pong by step parity (+1: the origin row of step 0) */
-  float* sdf;        /* [P+1] decoder outputs of the current step */
-  int32_t* counts;   /* [march_step + 2] active rays per step; zeroed by dist_render_depth_fwd */
+  int32_t* list_a;   /* [2*SEG] active ray list (ping), two row segments -- see below */
+  int32_t* list_b;   /* [2*SEG] active ray list (pong) */
+  float* pts;        /* [2][2*SEG][3] query points, ping-pong by step parity */
+  float* sdf;        /* [2*SEG] decoder outputs of the current step */
+  int32_t* counts;   /* [2*(march_step + 2)] active rays per step and segment; zeroed by dist_render_depth_fwd */
   float* sdf_origin; /* [1] sdf at the origin (filler samples, renderer.py:539-540) */
   float* entry0;     /* [P] true unit-sphere entry depth; == entry except in DIST_MARCH_PYRAMID, where `entry` holds the
                         depth the full-resolution march starts from (inherited from the 1/2-resolution parent ray) */
@@ -156,10 +159,12 @@ typedef struct dist_workspace {
   float* pyr_f;      /* (all three scale with n_views) */
   int32_t* pyr_i;
   uint8_t* pyr_b;
-  /* two-tier precision (dist_march_t.screen; all NULL otherwise).  T = ceil((P+1)/128): */
-  uint8_t* tile_mode;   /* [3][T] per-step tile hints, rotating (written one step ahead by the march update); zeroed by
-                           dist_render_depth_fwd */
-  uint8_t* seg_approx;  /* [2T] per 64-row half-tile of the current step: 1 = one-pass values */
+  /* Row segments of the march's query arrays: SEG = round_up(P + 1, 128); `list_a`, `list_b`, `sdf` hold 2*SEG entries,
+   * `pts` 2 x 2*SEG x 3, `counts` 2*(march_step + 2): counts[2s] / counts[2s+1] = rows of step s in segment 1 (rows
+   * [0, n1): rays predicted far from the surface) / segment 2 (rows [SEG, SEG + n2): the rest, and the origin at step 0).
+   * two-tier precision (dist_march_t.screen; NULL otherwise): */
+  uint8_t* seg_approx;  /* [2*SEG/64] per 64-row half-tile of the current step: 1 = one-pass values */
+  float* sprev;         /* [P] the ray's previous sdf (far / near prediction) */
   int32_t* rq_idx;      /* [P*B] re-query rows: local pixel * DIST_MAX_BUFFER + record slot */
   float* rq_pts;        /* [P*B][3] */
   float* rq_sdf;        /* [P*B] */
@@ -199,13 +204,15 @@ int dist_decoder_forward(const dist_net_t* net, int engine, const float* points,
                          const int32_t* n_dev, float clamp_dist, float* sdf, void* stream);
 
 /* dist_decoder_forward on the tensor-core engine with the two-tier precision the march uses (dist_march_t.screen), exposed
- * for the prepare-time accuracy check of the one-pass values and for tests: tile_mode[ceil(n/128)] (0 = try one fp16 pass
- * first, != 0 = three split-precision passes); a 64-row half-tile keeps its one-pass values when all of its rows have
- * |sdf| > screen_thresh, and is flagged in seg_approx[ceil(n/64)] (1 = one-pass values); all other rows are bit-identical
- * to dist_decoder_forward.  tile_counters (optional, [2]) += tile programs evaluated with one / three passes.
+ * for the prepare-time accuracy check of the one-pass values and for tests.  Rows [0, n_screen) are evaluated in 128-row
+ * tiles with ONE fp16 pass first; a 64-row half-tile keeps those values when all of its rows have |sdf| > screen_thresh
+ * and is flagged in seg_approx[row / 64] = 1; a tile with a nearer row in either half is re-evaluated with the three
+ * split-precision passes.  Rows [exact_offset, exact_offset + n_exact) (exact_offset a multiple of 128, >= n_screen) get the
+ * three passes directly.  Every row not flagged is bit-identical to dist_decoder_forward.  tile_counters (optional, [2])
+ * += tile programs evaluated with one / three passes.
  * No counterpart in the reference: its decoder (deep_sdf_decoder.py:80-111) is fp32 throughout. */
-int dist_decoder_forward_tiers(const dist_net_t* net, const float* points, int64_t n_host, const int32_t* n_dev,
-                               const uint8_t* tile_mode, float screen_thresh, float* sdf, uint8_t* seg_approx,
+int dist_decoder_forward_tiers(const dist_net_t* net, const float* points, int64_t n_screen, int64_t n_exact,
+                               int64_t exact_offset, float screen_thresh, float* sdf, uint8_t* seg_approx,
                                unsigned long long* tile_counters, void* stream);
 
 /* grad[i] = d clamp(sdf)/d xyz at points[i]; sdf (optional) receives the clamped value.

@@ -21,17 +21,21 @@ tc = importlib.import_module("dist-renderer_b200.tc")
 plan_mod = importlib.import_module("dist-renderer_b200.plan")
 
 
-def _tiers(plan, lat, pts, mode, thresh):
+def _tiers(plan, lat, pts, n_screen, n_exact, offset, thresh):
+    """dist_decoder_forward_tiers on rows [0, n_screen) (one pass first) and [offset, offset + n_exact) (three passes)."""
     lib, st = abi.lib(), torch.cuda.current_stream().cuda_stream
     tc.prepare(plan)
     b0, bl, _ = plan.fold(lat, st)
-    net = plan.c_net(b0, bl, bl * tc.S_ACT if bl is not None else None)
+    bl_tc = bl * tc.S_ACT if bl is not None else None       # keep alive: the descriptor holds raw addresses
+    net = plan.c_net(b0, bl, bl_tc)
     n = pts.shape[0]
     sdf = torch.full((n,), float("nan"), device="cuda")
     seg = torch.full(((n + 63) // 64,), 7, device="cuda", dtype=torch.uint8)
     cnt = torch.zeros(2, device="cuda", dtype=torch.int64)
-    abi.check(lib.dist_decoder_forward_tiers(net, abi.ptr(pts), n, None, abi.ptr(mode), float(thresh), abi.ptr(sdf),
+    abi.check(lib.dist_decoder_forward_tiers(net, abi.ptr(pts), n_screen, n_exact, offset, float(thresh), abi.ptr(sdf),
                                              abi.ptr(seg), abi.ptr(cnt), st))
+    torch.cuda.synchronize()
+    del b0, bl, bl_tc
     return sdf, seg, cnt
 
 
@@ -46,8 +50,8 @@ def test_tiers_kernel_contract(n):
     exact = pkg.decode_sdf(dec, lat, pts, clamp_dist=None, no_grad=True, engine="tc").reshape(-1)
     tiles = (n + 127) // 128
     thresh = 0.102
-    # (a) every tile tries one pass first
-    sdf, seg, cnt = _tiers(plan, lat, pts, torch.zeros(tiles, device="cuda", dtype=torch.uint8), thresh)
+    # (a) every row in the one-pass segment
+    sdf, seg, cnt = _tiers(plan, lat, pts, n, 0, 0, thresh)
     assert int(seg.max()) <= 1
     row_approx = seg.repeat_interleave(64)[:n].bool()
     assert bool(torch.equal(sdf[~row_approx], exact[~row_approx]))          # full-precision rows: bit-identical
@@ -59,16 +63,23 @@ def test_tiers_kernel_contract(n):
     seg_tile = torch.cat([seg, seg.new_ones(2 * tiles - seg.numel())]).reshape(-1, 2).bool().all(1)
     assert bool(seg_tile[far_tile].all())                                    # clearly far tiles keep their one-pass values
     assert int(cnt[0]) == tiles and int(cnt[1]) == int((~seg_tile).sum())    # failed tiles are redone, once
-    # (b) hints say "near": three passes directly, nothing flagged
-    sdf, seg, cnt = _tiers(plan, lat, pts, torch.ones(tiles, device="cuda", dtype=torch.uint8), thresh)
-    assert bool(torch.equal(sdf, exact)) and int(seg.max()) == 0 and cnt.tolist() == [0, tiles]
-    # (c) mixed hints
-    mode = (torch.arange(tiles, device="cuda") % 3 == 0).to(torch.uint8)
-    sdf, seg, cnt = _tiers(plan, lat, pts, mode, thresh)
-    row_approx = seg.repeat_interleave(64)[:n].bool()
-    assert bool(torch.equal(sdf[~row_approx], exact[~row_approx]))
-    seg_full = torch.cat([seg, seg.new_zeros(2 * tiles - seg.numel())]).reshape(-1, 2)
-    assert not bool(seg_full[mode.bool()].any())                              # hinted tiles are never one-pass
+    # (b) every row in the full-precision segment (placed at an offset): three passes directly, nothing flagged
+    off = 128 * 5
+    pts_b = torch.cat([torch.zeros(off, 3, device="cuda"), pts])
+    sdf, seg, cnt = _tiers(plan, lat, pts_b, 0, n, off, thresh)
+    assert bool(torch.equal(sdf[off:], exact)) and int(seg[off // 64:].max()) == 0 and cnt.tolist() == [0, tiles]
+    assert bool(torch.isnan(sdf[:off]).all())                                # rows outside both segments are untouched
+    # (c) both segments: the first n1 rows screened, the rest (stored behind a gap) at full precision
+    n1 = (n // 3) // 128 * 128 + min(17, n // 4)
+    off = (n1 + 127) // 128 * 128 + 256
+    pts_c = torch.cat([pts[:n1], torch.zeros(off - n1, 3, device="cuda"), pts[n1:]])
+    sdf, seg, cnt = _tiers(plan, lat, pts_c, n1, n - n1, off, thresh)
+    assert bool(torch.equal(sdf[off:], exact[n1:])) and int(seg[off // 64:].max()) == 0
+    a1 = seg[: (n1 + 63) // 64].repeat_interleave(64)[:n1].bool()
+    assert bool(torch.equal(sdf[:n1][~a1], exact[:n1][~a1]))
+    if bool(a1.any()):
+        assert float(exact[:n1][a1].abs().min()) > 0.1
+    assert int(cnt[0]) == (n1 + 127) // 128 and int(cnt[1]) >= (n - n1 + 127) // 128
 
 
 @pytest.mark.parametrize("kind", ["recursive", "pyramid_recursive", "trivial"])
