@@ -50,8 +50,11 @@ def load_peaks():
 
 
 def loss_of(out):
+    """A scalar of the rendered maps: depth summed over the silhouette + the min-|sdf| map (gradients reach every sample
+    the renderer selected).  Written with torch.where rather than boolean indexing: indexing would size its result on the
+    host, i.e. stall the stream in the middle of every step."""
     depth, normal, mask, min_sdf = out
-    return depth[mask.bool()].sum() + min_sdf.sum()
+    return torch.where(mask.bool(), depth, torch.zeros_like(depth)).sum() + min_sdf.sum()
 
 
 class ClockSampler(object):

@@ -100,23 +100,20 @@ __device__ __forceinline__ void sphere_geom(const float (&c)[3], const float (&r
   ex = entry + chord;
 }
 
-// sorted insertion into the per-ray top-B records (smallest |sdf| first); replaces topk over the step lists
-// (renderer.py:316-319)
+// Insertion into the per-ray top-B records (the B samples with the smallest |sdf|; replaces topk over the step lists,
+// renderer.py:316-319).  During the march the records are an UNORDERED set: a new sample replaces the record with the
+// largest |sdf| if it beats it -- one pass over B values and one record write per sample instead of shifting a sorted list
+// (the march update kernel is bound by exactly this traffic).  k_finalize sorts each ray's records once, ascending.
 __device__ __forceinline__ void topk_insert(const dist_workspace_t& ws, int P, int B, int lp, float sdf, float px, float py,
                                             float pz, float zafter, float zgen, int lvl) {
   const float asdf = fabsf(sdf);
-  int pos = B;
-  for (int b = 0; b < B; ++b)
-    if (asdf < fabsf(ws.top_sdf[(size_t)b * P + lp])) { pos = b; break; }
-  if (pos >= B) return;
-  for (int b = B - 1; b > pos; --b) {
-    ws.top_sdf[(size_t)b * P + lp] = ws.top_sdf[(size_t)(b - 1) * P + lp];
-    ws.top_zafter[(size_t)b * P + lp] = ws.top_zafter[(size_t)(b - 1) * P + lp];
-    ws.top_zgen[(size_t)b * P + lp] = ws.top_zgen[(size_t)(b - 1) * P + lp];
-    ws.top_lvl[(size_t)b * P + lp] = ws.top_lvl[(size_t)(b - 1) * P + lp];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) ws.top_pt[((size_t)b * 3 + k) * P + lp] = ws.top_pt[((size_t)(b - 1) * 3 + k) * P + lp];
+  int pos = 0;
+  float worst = -1.f;
+  for (int b = 0; b < B; ++b) {
+    const float a = fabsf(ws.top_sdf[(size_t)b * P + lp]);
+    if (a >= worst) { worst = a; pos = b; }
   }
+  if (!(asdf < worst)) return;
   ws.top_sdf[(size_t)pos * P + lp] = sdf;
   ws.top_zafter[(size_t)pos * P + lp] = zafter;
   ws.top_zgen[(size_t)pos * P + lp] = zgen;
@@ -448,24 +445,6 @@ __global__ void k_finalize(dist_march_t mp, dist_workspace_t ws, float* Zdepth, 
   const int lp = blockIdx.x * blockDim.x + threadIdx.x;
   if (lp >= P || !(ws.flags[lp] & 1)) return;
   const int B = mp.buffer_size;
-  {   // records re-queried at full precision changed value: restore the ascending-|sdf| order (the true minimum to slot 0)
-    bool any = false;
-    for (int b = 0; b < B; ++b) any |= (ws.top_lvl[(size_t)b * P + lp] & LVL_REQUERIED) != 0;
-    if (any) {
-      for (int a = 1; a < B; ++a)
-        for (int b = a; b > 0 && fabsf(ws.top_sdf[(size_t)b * P + lp]) < fabsf(ws.top_sdf[(size_t)(b - 1) * P + lp]); --b) {
-          const size_t x = (size_t)b * P + lp, y = (size_t)(b - 1) * P + lp;
-          float t = ws.top_sdf[x]; ws.top_sdf[x] = ws.top_sdf[y]; ws.top_sdf[y] = t;
-          t = ws.top_zafter[x]; ws.top_zafter[x] = ws.top_zafter[y]; ws.top_zafter[y] = t;
-          t = ws.top_zgen[x]; ws.top_zgen[x] = ws.top_zgen[y]; ws.top_zgen[y] = t;
-          const uint8_t l = ws.top_lvl[x]; ws.top_lvl[x] = ws.top_lvl[y]; ws.top_lvl[y] = l;
-          for (int k = 0; k < 3; ++k) {
-            const size_t px = ((size_t)b * 3 + k) * P + lp, py = ((size_t)(b - 1) * 3 + k) * P + lp;
-            t = ws.top_pt[px]; ws.top_pt[px] = ws.top_pt[py]; ws.top_pt[py] = t;
-          }
-        }
-    }
-  }
   // steps this ray's view executed before all of its rays had finished (the early break of renderer.py:562 is per render)
   const int S = ws.view_stat[VS_STRIDE * (lp / Pv) + VS_STEPS];
   int nreal = ws.nreal[lp];
@@ -490,6 +469,20 @@ __global__ void k_finalize(dist_march_t mp, dist_workspace_t ws, float* Zdepth, 
     }
     nreal = B;
     ws.nreal[lp] = B;
+  }
+  {   // the records are an unordered set until here: ascending |sdf| (stable), the minimum to slot 0 (renderer.py:316-319)
+    for (int a = 1; a < B; ++a)
+      for (int b = a; b > 0 && fabsf(ws.top_sdf[(size_t)b * P + lp]) < fabsf(ws.top_sdf[(size_t)(b - 1) * P + lp]); --b) {
+        const size_t x = (size_t)b * P + lp, y = (size_t)(b - 1) * P + lp;
+        float t = ws.top_sdf[x]; ws.top_sdf[x] = ws.top_sdf[y]; ws.top_sdf[y] = t;
+        t = ws.top_zafter[x]; ws.top_zafter[x] = ws.top_zafter[y]; ws.top_zafter[y] = t;
+        t = ws.top_zgen[x]; ws.top_zgen[x] = ws.top_zgen[y]; ws.top_zgen[y] = t;
+        const uint8_t l = ws.top_lvl[x]; ws.top_lvl[x] = ws.top_lvl[y]; ws.top_lvl[y] = l;
+        for (int k = 0; k < 3; ++k) {
+          const size_t px = ((size_t)b * 3 + k) * P + lp, py = ((size_t)(b - 1) * 3 + k) * P + lp;
+          t = ws.top_pt[px]; ws.top_pt[px] = ws.top_pt[py]; ws.top_pt[py] = t;
+        }
+      }
   }
   const float s0 = ws.top_sdf[lp];
   const float entry = ws.entry[lp];

@@ -39,10 +39,13 @@ namespace {
 // activation blocks (A_FULL) and for weight stages (W_FULL) per layer: dbg_out[256 + 2 m], dbg_out[257 + 2 m]
 #ifdef DIST_TC_TIMELINE
 #define TL_BEGIN() const long long tl_c0 = clock64()
-#define TL_END(slot_) do { if (io.dbg_out && cluster_id == 0 && i == 1 && lane == 0) io.dbg_out[256 + 2 * m + (slot_)] += clock64() - tl_c0; } while (0)
+#define TL_TILE (c1 > 0 ? 2 : 1)     /* the traced tile: the cluster's second tile / second pair */
+#define TL_END(slot_) do { if (io.dbg_out && cluster_id == 0 && i == TL_TILE && lane == 0) io.dbg_out[256 + 2 * m + (slot_)] += clock64() - tl_c0; } while (0)
+#define TL_MARK(idx_) do { if (io.dbg_out && cluster_id == 0 && i == TL_TILE && lane == 0) io.dbg_out[idx_] = clock64(); } while (0)
 #else
 #define TL_BEGIN() do {} while (0)
 #define TL_END(slot_) do {} while (0)
+#define TL_MARK(idx_) do {} while (0)
 #endif
 
 constexpr int NST = 6;                 // weight ring stages
@@ -52,7 +55,7 @@ constexpr int OFF_BAR = OFF_W + NST * STAGE_BYTES;   // 229376
 constexpr int OFF_PART = OFF_BAR + 512;              // per-row partial sums [64][8] (8 threads share a row)
 constexpr int OFF_ROWD = OFF_PART + 2048;            // per-row scalar [64]
 constexpr int OFF_FAIL = OFF_ROWD + 256;             // two-tier precision: [near flag u32][pad][fail bitmap, FAIL_WORDS u32]
-constexpr int FAIL_WORDS = 32;                       // 1024 tiles per cluster and launch (7 M rows on 74 clusters)
+constexpr int FAIL_WORDS = 32;                       // 1024 tiles per cluster and launch (9 M rows on 74 clusters)
 constexpr int SMEM_BYTES = OFF_FAIL + 16 + 4 * FAIL_WORDS;   // 232336 (limit 232448)
 constexpr int NTHREADS = 640;                        // 4 service warps + 16 epilogue warps
 constexpr int MAX_PROG = 2 * 10;                     // forward + transposed chain, at most 10 tensor-core layers each
@@ -198,6 +201,14 @@ __device__ __forceinline__ void store_group(uint8_t* smem, int feat0, int row, c
   }
 }
 
+// pair mode: hi halves only, into the activation region at byte offset `region` (OFF_AHI: tile 0, OFF_ALO: tile 1)
+__device__ __forceinline__ void store_group_hi(uint8_t* smem, int region, int feat0, int row, const float* x) {
+  __half2 h[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(x[2 * i], x[2 * i + 1]);
+  *reinterpret_cast<uint4*>(smem + region + (feat0 >> 3) * 1024 + row * 16) = *reinterpret_cast<uint4*>(h);
+}
+
 // --------------------------------------------------------------------------------------------- kernel
 // MODE 0: forward (sdf).  MODE 1: forward + transposed chain -> d clamp(sdf)/d xyz.  MODE 2: backward replay with per-row
 // upstream coefficients: d/dxyz per row and the row-summed pre-activation gradients of layer 0 / the latent_in layer.
@@ -245,10 +256,18 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
   const uint32_t fail_addr = sbase + OFF_FAIL + 16;
   auto tile_of = [&](int i) -> int64_t { return cluster_id + (int64_t)i * n_clusters; };
   auto tile_exact = [&](int64_t t) -> bool { return !screening || t >= tiles1; };
+  // One-pass tiles are processed TWO AT A TIME ("pair mode"): the second tile's activations live where a full-precision tile
+  // keeps its lo halves (OFF_ALO), its accumulators in the second TMEM buffer, and both tiles consume every weight stage --
+  // the weight stream and the barrier traffic are paid once per 256 rows, and the tensor pipe has the other tile's MMAs to
+  // run while one tile's epilogue is on the critical path.  c1 = this cluster's one-pass tiles (the first c1 of its list).
+  const int c1 = (screening && cluster_id < tiles1) ? (int)((tiles1 - cluster_id + n_clusters - 1) / n_clusters) : 0;
   // next tile index of this cluster after i (i = -1: the first), -1 when exhausted.  phase 0: all tiles; phase 1: tiles
   // whose fail bit is set in this CTA's or the peer's bitmap (read through distributed shared memory)
   auto next_tile = [&](int phase, int i) -> int {
-    if (phase == 0) return (i + 1 < cnt) ? i + 1 : -1;
+    if (phase == 0) {     // pairs (i, i + 1) inside [0, c1), single tiles after that
+      const int j = (i < 0) ? 0 : ((i < c1) ? min(i + 2, c1) : i + 1);
+      return (j < cnt) ? j : -1;
+    }
     int j = i + 1;
     while (j < cnt) {
       const uint32_t w = (fail_words[j >> 5] | ld_dsmem_u32(fail_addr + 4 * (j >> 5), rank ^ 1u)) >> (j & 31);
@@ -264,7 +283,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
     for (int c = 0; c < 16; ++c) mbar_init(A_FREE(c), 1);
     for (int b = 0; b < 2; ++b) { mbar_init(D_FULL(b, 0), 1); mbar_init(D_FULL(b, 1), 1); }
     mbar_init(FIN, 32);                                     // 16 epilogue warps x 2 CTAs
-    *near_flag = 0u;
+    near_flag[0] = 0u; near_flag[1] = 0u;
     for (int w = 0; w < FAIL_WORDS; ++w) fail_words[w] = 0u;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -287,7 +306,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
       const uint32_t bar_leader_mask = 0xFEFFFFFFu;
       for (int phase = 0; phase < 2; ++phase) {
         for (int i = next_tile(phase, -1); i >= 0; i = next_tile(phase, i)) {
-          const bool exact = (phase == 1) || tile_exact(tile_of(i));
+          const bool exact = !(phase == 0 && i < c1);      // one-pass tiles come in pairs that share one weight stream
           for (int m = 0; m < n_prog; ++m) {
             const int kc32 = P.L[m].kc32, sb = P.L[m].stage_base;
             // full precision: one ring slot = one 32-wide K chunk, [hi 8 KB][lo 8 KB] per CTA.
@@ -339,16 +358,20 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
       const uint64_t b_0 = make_desc(sbase + OFF_W, 2048, 128);
       uint32_t G = 0, a_phase = 0, fin_phase = 0, w_slot = 0, w_phase = 0;
       uint32_t d_first = 1;
+      bool prev_pair = false;
       for (int phase = 0; phase < 2; ++phase) {
       for (int i = next_tile(phase, -1); i >= 0; i = next_tile(phase, i)) {
         const int64_t t = tile_of(i);
-        const bool exact = (phase == 1) || tile_exact(t);   // one-pass tiles issue A_hi W_hi only
+        const bool exact = !(phase == 0 && i < c1);   // pair mode: two one-pass tiles, A_hi W_hi only
+        const bool has_b = !exact && (i + 1 < c1);    // (an odd count leaves the last pair with one tile)
         (void)t;
         for (int m = 0; m < n_prog; ++m, ++G) {
           const int kc32 = P.L[m].kc32, nh = P.L[m].nh;
-          const uint32_t buf = G & 1;
-          // the last accumulator of the previous tile lives in this buffer until its epilogue drained it
-          if (m == 1 && !d_first) { mbar_wait_cluster(FIN, fin_phase); fin_phase ^= 1; }
+          const uint32_t buf = exact ? (G & 1) : 0u;
+          // The last accumulator of the previous tile lives in a TMEM buffer until its epilogue drained it (FIN).  Single tiles
+          // ping-pong between the two buffers layer by layer, so layer 0 may start early and only layer 1 waits; a pair uses
+          // both buffers in every layer, so a pair -- and the tile after a pair -- waits before its layer 0.
+          if (!d_first && m == ((!exact || prev_pair) ? 0 : 1)) { mbar_wait_cluster(FIN, fin_phase); fin_phase ^= 1; }
           // N-half outer, K block inner: half 0 of the accumulator completes while half 1 is still being computed, so
           // its epilogue (the first A blocks of the next layer) overlaps the second pass.  A_FREE(kc) tells the epilogue
           // when the last pass has consumed A block kc and its slot may be overwritten in place.
@@ -364,6 +387,12 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
                 if (h == 0) {
                   TL_BEGIN();
                   for (int c = 0; c < 2 * nsl; ++c) mbar_wait_cluster(A_FULL(kc + c), (a_phase >> (kc + c)) & 1);
+                  if (kc == 0) TL_MARK(8 + m * 4 + 0);
+                  // A pair keeps its accumulators in fixed TMEM buffers (no ping-pong between layers): the first MMA of this
+                  // pass overwrites N-half 0 of the previous layer, which the epilogue has read completely only once ALL the
+                  // blocks made from it (0..7) are written -- wait for those too (they are waited on again, and consumed, below)
+                  if (kc == 0)
+                    for (int c = 2 * nsl; c < min(8, kc32); ++c) mbar_wait_cluster(A_FULL(c), (a_phase >> c) & 1);
                   a_phase ^= (nsl == 2 ? 15u : 3u) << kc;
                   TL_END(0);
                 }
@@ -384,14 +413,18 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
                 if (elect_one()) {
                   for (int u = 0; u < nsl; ++u) {
                     const uint32_t slot = u ? slot1 : slot0;
+                    for (int ts = 0; ts < (has_b ? 2 : 1); ++ts) {     // both tiles of the pair read this weight slot
+                      const uint64_t a_base = ts ? a_lo0 : a_hi0;      // tile 1's activations live in the lo region
+                      const uint32_t d_ts = d_addr + ts * 256;
 #pragma unroll
-                    for (int c = 0; c < 2; ++c) {
+                      for (int c = 0; c < 2; ++c) {
 #pragma unroll
-                      for (int ks = 0; ks < 2; ++ks) {
-                        const int kk = kc + 2 * u + c;
-                        const uint64_t a_off = (uint64_t)((kk * 4 + ks * 2) * 64);
-                        const uint64_t b_off = (uint64_t)(slot * (STAGE_BYTES / 16) + c * 512 + ks * 256);
-                        mma_f16_2cta(d_addr, a_hi0 + a_off, b_0 + b_off, idesc, (kk | ks) ? 1u : 0u);
+                        for (int ks = 0; ks < 2; ++ks) {
+                          const int kk = kc + 2 * u + c;
+                          const uint64_t a_off = (uint64_t)((kk * 4 + ks * 2) * 64);
+                          const uint64_t b_off = (uint64_t)(slot * (STAGE_BYTES / 16) + c * 512 + ks * 256);
+                          mma_f16_2cta(d_ts, a_base + a_off, b_0 + b_off, idesc, (kk | ks) ? 1u : 0u);
+                        }
                       }
                     }
                     commit_mc(W_EMPTY(slot));
@@ -400,6 +433,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
                   if (kc + 4 >= kc32) commit_mc(D_FULL(buf, h));
                 }
                 __syncwarp();
+                if (kc + 4 >= kc32 && last_pass) TL_MARK(8 + m * 4 + 1);
               }
             } else
             for (int kc = 0; kc < kc32; kc += 2) {
@@ -451,6 +485,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
           }
         }
         d_first = 0;
+        prev_pair = !exact;
       }
         if (phase == 0) {
           if (!screening) break;
@@ -540,13 +575,172 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
     };
 
     unsigned int n_tiles_1pass = 0, n_tiles_3pass = 0;   // tile programs this cluster evaluated (rank 0, warp 4, lane 0)
+
+    // ---------------------------------------------------------------- pair mode (two one-pass tiles in lockstep, MODE 0)
+    float qx = 0.f, qy = 0.f, qz = 0.f;      // this thread's point of the pair's second tile
+    auto load_points_pair = [&](int i) {
+      load_point(tile_of(i));
+      const int64_t tb = tile_of(i + 1);
+      const int64_t grb = row0_of(tb) + rank * 64 + row;
+      if (i + 1 < c1 && grb < n1) { qx = io.points[grb * 3]; qy = io.points[grb * 3 + 1]; qz = io.points[grb * 3 + 2]; }
+      else { qx = qy = qz = 0.f; }
+    };
+    auto layer0_pair = [&]() {     // layer 0 of both tiles on CUDA cores: hi halves into the two activation regions
+      const int kblocks = P.L[0].kc32;
+      const int nh0 = (P.N0 + 255) >> 8;
+      for (int h = 0; h < nh0; ++h) {
+        const int kb = 8 * h + 4 * q + ch;
+        if (kb >= kblocks) continue;
+        const int f0 = 32 * kb;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float xa[8], xb[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int f = f0 + 8 * g + e;
+            float va = 0.f, vb = 0.f;
+            if (f < P.N0) {
+              const float wx = __ldg(P.w0 + f), wy = __ldg(P.w0 + P.N0p4 + f), wz = __ldg(P.w0 + 2 * P.N0p4 + f), b = __ldg(P.bias0 + f);
+              va = fmaxf(fmaf(wz, pz, fmaf(wy, py, wx * px)) + b, 0.f);
+              vb = fmaxf(fmaf(wz, qz, fmaf(wy, qy, wx * qx)) + b, 0.f);
+            } else if (P.first_append && f < P.N0 + 3) {
+              va = (f == P.N0) ? px : ((f == P.N0 + 1) ? py : pz);
+              vb = (f == P.N0) ? qx : ((f == P.N0 + 1) ? qy : qz);
+            }
+            xa[e] = va * sA; xb[e] = vb * sA;
+          }
+          store_group_hi(smem, OFF_AHI, f0 + 8 * g, row, xa);
+          store_group_hi(smem, OFF_ALO, f0 + 8 * g, row, xb);
+        }
+        signal_block(kb);
+      }
+    };
+    // what the next tile needs before the current one is drained: its points, then (A being free) its layer 0
+    auto prefetch_points = [&](int phase, int inext) {
+      if (inext < 0) return;
+      if (phase == 0 && inext < c1) load_points_pair(inext); else load_point(tile_of(inext));
+    };
+    auto start_layer0 = [&](int phase, int inext) {
+      if (inext < 0) return;
+      if (phase == 0 && inext < c1) layer0_pair(); else layer0();
+    };
+    // the whole forward program of one pair (tiles i and, if has_b, i + 1 of this cluster's list)
+    auto run_pair = [&](int i, int inext, bool has_b) {
+      const int64_t ta = tile_of(i), tb = tile_of(i + 1);
+      const int64_t gra = row0_of(ta) + rank * 64 + row, grb = row0_of(tb) + rank * 64 + row;
+      const bool oka = gra < n1, okb = has_b && grb < n1;
+      float dota = 0.f, dotb = 0.f;
+      for (int m = 0; m < n_mma; ++m, ++G) {
+        const bool last = (m == n_mma - 1);
+        const int LN = P.L[m].N, Lnh = P.L[m].nh, Lapp = P.L[m].app_xyz;
+        const float cscale = P.L[m].inv_scale;
+        const float* Lbias = P.L[m].bias;
+        const int kc32_cur = P.L[m].kc32;
+        const int kblocks_next = last ? 0 : P.L[m + 1].kc32;
+        auto wait_h = [&](int h) {      // a pair always accumulates in TMEM buffer 0 (tile 0) and 1 (tile 1); barrier set 0
+          mbar_wait(D_FULL(0, h), (d_phase >> h) & 1);
+          d_phase ^= (1u << h);
+          tc_fence_after();
+        };
+        if (last) {
+          prefetch_points(0, inext);
+          for (int h = 0; h < Lnh; ++h) wait_h(h);      // all MMAs of the pair are complete: both activation regions are free
+          start_layer0(0, inext);
+        }
+        for (int h = 0; h < Lnh; ++h) {
+          const int kb = 8 * h + 4 * q + ch;
+          const int fb = 32 * kb;
+          const bool need_store = !last && kb < kblocks_next;
+          const bool process = last ? (fb < LN) : need_store;
+          if (!last) wait_h(h);
+          if (!process) continue;
+          const bool interior = (fb + 32 <= LN);
+          if (h == 0 && rank == 0 && warp == 4) TL_MARK(8 + m * 4 + 2);
+          if (need_store && kb < kc32_cur) mbar_wait(A_FREE(kb), (free_phase >> kb) & 1);   // the last pass has read block kb
+          for (int ts = 0; ts < (has_b ? 2 : 1); ++ts) {
+            float v[32];
+            tmem_ld32(tmem + lane_base + ts * 256 + h * 128 + 32 * ch, v);
+            if (interior) {
+#pragma unroll
+              for (int j4 = 0; j4 < 8; ++j4) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(Lbias + fb) + j4);
+                v[4 * j4] = fmaxf(fmaf(v[4 * j4], cscale, b4.x), 0.f);
+                v[4 * j4 + 1] = fmaxf(fmaf(v[4 * j4 + 1], cscale, b4.y), 0.f);
+                v[4 * j4 + 2] = fmaxf(fmaf(v[4 * j4 + 2], cscale, b4.z), 0.f);
+                v[4 * j4 + 3] = fmaxf(fmaf(v[4 * j4 + 3], cscale, b4.w), 0.f);
+              }
+            } else {
+              const float ax = ts ? qx : px, ay = ts ? qy : py, az = ts ? qz : pz;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const int f = fb + j;
+                float a = 0.f;
+                if (f < LN) a = fmaxf(fmaf(v[j], cscale, __ldg(Lbias + f)), 0.f);
+                else if (Lapp && f < LN + 3) a = ((f == LN) ? ax : ((f == LN + 1) ? ay : az)) * sA;
+                v[j] = a;
+              }
+            }
+            if (last) {
+              float d = 0.f;
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (interior || fb + j < LN) d = fmaf(v[j], __ldg(P.wlast + fb + j), d);
+              if (ts) dotb += d; else dota += d;
+            } else {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) store_group_hi(smem, ts ? OFF_ALO : OFF_AHI, fb + 8 * g, row, &v[8 * g]);
+            }
+          }
+          if (need_store) signal_block(kb);
+        }
+        if (rank == 0 && warp == 4) TL_MARK(8 + m * 4 + 3);
+        free_phase ^= (kc32_cur >= 16) ? 0xFFFFu : ((1u << kc32_cur) - 1u);
+        if (last) {
+          // both accumulators are in registers: release TMEM for the next tile, then finish the two dot products
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(FIN, 0);
+          for (int ts = 0; ts < (has_b ? 2 : 1); ++ts) {
+            part[row * 8 + pslot] = ts ? dotb : dota;
+            epi_bar_sync();
+            if (pslot == 0) {
+              const float sv = row_sum8() * (1.f / sA) + __ldg(P.blast);
+              float o = tanhf(sv);
+              if (P.use_tanh) o = tanhf(o);
+              float oc = o;
+              if (io.clamp_dist > 0.f) oc = fminf(fmaxf(o, -io.clamp_dist), io.clamp_dist);
+              const bool ok = ts ? okb : oka;
+              if (ok && io.sdf) io.sdf[ts ? grb : gra] = oc;
+              if (ok && !(fabsf(o) > io.screen_thresh)) near_flag[ts] = 1u;   // may be inside the clamp band (or NaN)
+            }
+            epi_bar_sync();
+          }
+          if (ew == 0 && lane == 0) {
+            for (int ts = 0; ts < (has_b ? 2 : 1); ++ts) {
+              const bool fail = near_flag[ts] != 0u;
+              if (fail) { fail_words[(i + ts) >> 5] |= 1u << ((i + ts) & 31); near_flag[ts] = 0u; }   // redo in phase 1
+              const int64_t r0 = row0_of(ts ? tb : ta) + rank * 64;
+              if (io.seg_approx && r0 < n1) io.seg_approx[r0 >> 6] = fail ? 0 : 1;
+              ++n_tiles_1pass;
+            }
+          }
+        }
+      }
+    };
+
     for (int phase = 0; phase < 2; ++phase) {
     int i = next_tile(phase, -1);
-    if (i >= 0) { load_point(tile_of(i)); layer0(); }
+    prefetch_points(phase, i);
+    start_layer0(phase, i);
     while (i >= 0) {
       const int64_t t = tile_of(i);
       const int inext = next_tile(phase, i);
-      const bool exact = (phase == 1) || tile_exact(t);
+      if (MODE == 0 && phase == 0 && i < c1) {     // a pair of one-pass tiles
+        run_pair(i, inext, i + 1 < c1);
+        i = inext;
+        continue;
+      }
+      const bool exact = true;
       const int64_t gr = row0_of(t) + rank * 64 + row;
       const bool row_ok = gr < lim_of(t);
       float dot = 0.f, rowscale = 0.f, dx = 0.f, dy = 0.f, dz = 0.f;
@@ -572,7 +766,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
         };
         // the next tile's points are fetched before the wait so that their latency hides behind the last MMAs
         // (px/py/pz of this tile are no longer needed: xyz is only appended in earlier forward layers)
-        if (prog_last && inext >= 0) load_point(tile_of(inext));
+        if (prog_last) prefetch_points(phase, inext);
         if (prog_last) for (int h = 0; h < Lnh; ++h) wait_half(h);   // all MMAs of the tile done before A is recycled
 #ifdef DIST_TC_TIMELINE
         const bool dbg_rec = io.dbg_out && cluster_id == 0 && rank == 0 && warp == 4 && lane == 0 && t == cluster_id + n_clusters;
@@ -582,7 +776,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
         if (prog_last) {
           // all MMAs of this tile are complete: A is free -> start the next tile's layer 0 before draining D
           if (MODE != 0) { mk0s[0] = mk[0][0]; mk0s[1] = mk[0][1]; }
-          if (inext >= 0) layer0();
+          start_layer0(phase, inext);
         }
         const int kblocks_next = prog_last ? 0 : P.L[m + 1].kc32;
         // net layer whose ReLU mask gates the values produced here (transposed chain): l-1 with l = 2 n_mma - m
