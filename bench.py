@@ -229,16 +229,20 @@ def config_of(n_gpus, side=HW_BASE):
 
 
 def ncu_traffic(tc):
-    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel on the same 262,144-row batch,
-    from the committed `ncu --set full` capture (profiles/r1_*_raw.csv); None when no capture is committed."""
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the committed `ncu --set full`
+    capture (profiles/r2_tc_raw.csv, row 3: mlp_tc_kernel<0> on a dense march step's mix of 262,144 rows, 60 % in the
+    one-pass segment); None when no capture is committed (the fp32 engine has none this round)."""
     import csv
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles",
-                        "r1_tc_fwd_raw.csv" if tc else "r1_simt_fwd_raw.csv")
+    if not tc:
+        return None
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r2_tc_raw.csv")
     try:
         rows = list(csv.reader(open(path)))
         unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
         col = {h: i for i, h in enumerate(rows[0])}
-        return sum(float(rows[2][col[k]]) * unit[rows[1][col[k]]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+        r = rows[4]
+        assert "mlp_tc_kernel<0>" in r[col["Kernel Name"]]
+        return sum(float(r[col[k]]) * unit[rows[1][col[k]]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
     except Exception:
         return None
 
@@ -493,7 +497,7 @@ def main():
                              "frac_of_burst_peak": isolated / peak_burst, "issued_frac_of_burst_peak": passes * isolated / peak_burst,
                              "burst_peak": peak_burst,
                              "note": "one 262,144-row forward launch at full split precision (3 fp16 MMA passes), after a cooldown"},
-                "traffic_note": "dram bytes of one 262,144-row launch (ncu --set full capture under profiles/)",
+                "traffic_note": "dram bytes of one 262,144-row launch with a dense march step's tier mix (ncu --set full, profiles/r2_tc_raw.csv)",
                 "note": "achieved counts USEFUL flops (F per folded decoder row, 2F per gradient row) over the event-timed "
                         "decoder kernels of the running step; the tensor-core engine issues 3 fp16 MMA passes per logical GEMM "
                         "(split-fp16, fp32-level parity) on rows that need them",

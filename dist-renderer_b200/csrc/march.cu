@@ -493,7 +493,10 @@ __global__ void k_finalize(dist_march_t mp, dist_workspace_t ws, float* Zdepth, 
   min_sdf[lp] = real0 ? s0 : so;  // renderer.py:382-390 (value of the re-query at the min-|sdf| point)
   // renderer.py:407-408
   float zz = ws.top_zafter[lp] + (1.f - mp.ratio) * clampf(s0, mp.clamp_dist);
-  if (mp.replay_grad_rounding) {  // renderer.py:414-417: z - s.detach()*ratio + s*ratio, value-neutral up to rounding
+  // renderer.py:414-417: z - s.detach()*ratio + s*ratio, value-neutral up to rounding; per view (bit v, bit 31 = every view):
+  // a view rendered with no_grad_depth skips the additions (renderer.py:413), and its last bit with them
+  const int vw = lp / Pv;
+  if ((mp.replay_grad_rounding >> 31) & 1 || (vw < 31 && ((mp.replay_grad_rounding >> vw) & 1))) {
     for (int b = 0; b < B; ++b) {
       const float sb = ws.top_sdf[(size_t)b * P + lp];
       const float s = clampf((sb != 1.0f) ? sb : so, mp.clamp_dist);

@@ -55,7 +55,7 @@ class _RenderDepthFn(torch.autograd.Function):
         cam_pos = ren.get_camera_location(Rd, T.detach().float()).contiguous()  # renderer.py:186
         cam = ren._c_camera(Rd, cam_pos, opts["use_transform"])
         mp = _abi.March(ren.march_step, B, _MARCH[opts["kind"]], 1 if opts["kind"] != "pyramid_recursive" else 0,
-                        ren.ray_marching_ratio, ren.threshold, float(opts["clamp_dist"]), 1 if opts["replay"] else 0)
+                        ren.ray_marching_ratio, ren.threshold, float(opts["clamp_dist"]), opts["replay"])
         pyr = opts["kind"] == "pyramid_recursive"
         if pyr:
             mp.coarse_steps[0], mp.coarse_steps[1] = ren._coarse_steps()
@@ -399,9 +399,19 @@ class SDFRenderer(object):
     def render_depth(self, latent, R, T, clamp_dist=0.1, sample_index_type='min_abs', profile=False, no_grad=False,
                      no_grad_depth=False, no_grad_mask=False, no_grad_camera=False, ray_marching_type='recursive',
                      use_transform=True, check_empty=True):
-        """(Zdepth[P], valid_mask[P] bool, min_sdf[P]) -- renderer.py:836-878."""
+        """(Zdepth[P], valid_mask[P] bool, min_sdf[P]) -- renderer.py:836-878.
+
+        On a multi-view renderer (``_fused_child``: R (V,3,3), T (V,3)) ``no_grad_depth`` may be a sequence of V flags: the
+        views are marched together, each with the depth-gradient semantics of its own flag (`render_warp` renders its
+        second view with no_grad_depth=True, renderer_warp.py:109)."""
         if no_grad:
             no_grad_depth, no_grad_mask, no_grad_camera = True, True, True
+        ngd_views = None
+        if isinstance(no_grad_depth, (list, tuple)):
+            if len(no_grad_depth) != self.n_views or self.n_views > 31:
+                raise ValueError("no_grad_depth needs one flag per view (at most 31 views)")
+            ngd_views = [bool(f) for f in no_grad_depth]
+            no_grad_depth = all(ngd_views)
         if sample_index_type != 'min_abs':
             raise NotImplementedError("sample_index_type='%s' is not implemented (only 'min_abs')" % sample_index_type)
         if ray_marching_type == 'pyramid_recursive':
@@ -420,7 +430,10 @@ class SDFRenderer(object):
             cam_levels = {"recursive": 0, "pyramid_recursive": 2}.get(ray_marching_type, 3)
         opts = dict(kind=ray_marching_type, clamp_dist=clamp_dist, use_transform=use_transform, engine=self.engine,
                     want_depth_grad=any_grad and not no_grad_depth, want_mask_grad=any_grad and not no_grad_mask,
-                    cam_levels=cam_levels if any_grad else 0, replay=not no_grad_depth)
+                    cam_levels=cam_levels if any_grad else 0,
+                    # dist_march_t.replay_grad_rounding: bit 31 = every view, else one bit per view
+                    replay=(sum(1 << v for v, f in enumerate(ngd_views) if not f) if ngd_views is not None
+                            else (0 if no_grad_depth else -2147483648)))
         Zdepth, mask, min_sdf, hit = _RenderDepthFn.apply(latent, R, T, self, opts)
         if check_empty:
             self._raise_if_empty()
@@ -431,6 +444,9 @@ class SDFRenderer(object):
             min_sdf = torch.where(hit, min_sdf, d + self.threshold - self.radius)
         if no_grad_depth:
             Zdepth = Zdepth.detach()
+        elif ngd_views is not None and any(ngd_views):
+            Zv = Zdepth.reshape(self.n_views, self.Pv)
+            Zdepth = torch.stack([Zv[v].detach() if f else Zv[v] for v, f in enumerate(ngd_views)], 0).reshape(-1)
         if no_grad_mask and not (R.requires_grad or T.requires_grad):
             min_sdf = min_sdf.detach()
         return Zdepth, mask.bool(), min_sdf

@@ -3,7 +3,7 @@
 Drop-in for `core/sdfrenderer/renderer_warp.py:13-144`: view 1 is rendered with depth
 gradients, view 2 without; the hit points of view 1 are reprojected into view 2, filtered by a depth-consistency test
 against view 2's rendered depth, and the colours of both images are compared at the corresponding pixels (L1).
-All decoder work (two `render_depth` calls + one `render_normal`) runs on the engines of `renderer.SDFRenderer`;
+All decoder work (ONE two-view march + one `render_normal`) runs on the engines of `renderer.SDFRenderer`;
 the reprojection / bilinear sampling is a handful of elementwise PyTorch ops on (3, N) tensors and stays in PyTorch,
 exactly as in the reference, so the loss carries gradients to `latent`, `R1`, `T1`.
 
@@ -80,8 +80,15 @@ class SDFRenderer_warp(SDFRenderer):
         """renderer_warp.py:103-144.  Returns (loss_color, color_valid_1, color_valid_2, valid_mask1, valid_mask2,
         min_sdf_sample1, min_sdf_sample2, Znormal1, depth1_rendered)."""
         h, w = self.img_hw
-        out1 = self.render_depth(latent, R1, T1, clamp_dist=clamp_dist, profile=profile)
-        out2 = self.render_depth(latent, R2, T2, clamp_dist=clamp_dist, profile=profile, no_grad_depth=True)
+        # renderer_warp.py:108-109 renders the two views one after the other (the second with no_grad_depth=True); here
+        # both are marched TOGETHER (dist_camera_t.n_views = 2, per-view depth-gradient flag): one compaction list, one
+        # decoder launch per step, one latency-bound tail -- with the maps of two separate render_depth calls bit for bit
+        pair = self._fused_child(2)
+        Z, M, S = pair.render_depth(latent, torch.stack([R1, R2], 0), torch.stack([T1, T2], 0), clamp_dist=clamp_dist,
+                                    profile=profile, no_grad_depth=[False, True], check_empty=False)
+        P = h * w
+        out1, out2 = (Z[:P], M[:P], S[:P]), (Z[P:], M[P:], S[P:])
+        pair._raise_if_empty()
         Zdepth1, valid_mask1, min_sdf1 = out1
         Zdepth2, valid_mask2, min_sdf2 = out2
         min_sdf1, min_sdf2 = min_sdf1.reshape(h, w), min_sdf2.reshape(h, w)

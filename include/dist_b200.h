@@ -108,7 +108,9 @@ typedef struct dist_march {
   float ratio;                /* ray_marching_ratio */
   float threshold;
   float clamp_dist;
-  int32_t replay_grad_rounding; /* 1: reproduce the value-neutral (z - a) + a roundings of renderer.py:414-417 */
+  int32_t replay_grad_rounding; /* reproduce the value-neutral (z - a) + a roundings of renderer.py:414-417 (a render with depth
+                                   gradients adds and subtracts each selected sample; no_grad_depth skips it, renderer.py:413).
+                                   Bit mask: bit 31 = every view, else bit v = view v of a multi-view call (v < 31) */
   int32_t coarse_steps[2];    /* DIST_MARCH_PYRAMID: trivial steps at 1/4 and 1/2 resolution (renderer.py:13 march_step_list) */
   int32_t screen;             /* two-tier precision of the march on DIST_ENGINE_TC (0 = every row at full precision): a row
                                  whose sdf is safely beyond the clamp, |sdf| > clamp_dist + screen_margin, steps by exactly

@@ -241,6 +241,42 @@ def test_render_warp_matches_oracle():
     assert abs(float(out[0]) - float(gold["loss"])) < 2e-3 * float(gold["loss"])
 
 
+def test_render_warp_marches_both_views_together():
+    """next-1: render_warp issues ONE two-view march (per-view depth-gradient flag) whose maps are those of the reference's
+    two separate render_depth calls (renderer_warp.py:108-109) bit for bit, with half the launches."""
+    import importlib
+    warp = importlib.import_module("dist-renderer_b200.renderer_warp")
+    abi = importlib.import_module("dist-renderer_b200._abi")
+    lib = abi.lib()
+    hw, K, (R1, T1), (R2, T2), img1, img2 = cases.warp_case()
+    rw = warp.SDFRenderer_warp(gu.gpu_decoder("B"), K, img_hw=hw)
+    lat = synth.make_latent().cuda().requires_grad_(True)
+    R1, T1, R2, T2 = R1.cuda(), T1.cuda(), R2.cuda(), T2.cuda()
+    rw.render_depth(lat, R1, T1)                      # engine preparation outside the counted region
+    n0 = lib.dist_launch_count()
+    a = rw.render_depth(lat, R1, T1)
+    b = rw.render_depth(lat, R2, T2, no_grad_depth=True)
+    n1 = lib.dist_launch_count()
+    pair = rw._fused_child(2)
+    Z, M, S = pair.render_depth(lat, torch.stack([R1, R2]), torch.stack([T1, T2]), no_grad_depth=[False, True])
+    n2 = lib.dist_launch_count()
+    P = hw[0] * hw[1]
+    for x, y in zip(a, (Z[:P], M[:P], S[:P])):
+        assert torch.equal(x.detach(), y.detach())
+    for x, y in zip(b, (Z[P:], M[P:], S[P:])):
+        assert torch.equal(x.detach(), y.detach())
+    assert (n2 - n1) < 0.6 * (n1 - n0)
+    # gradients: only view 1's depth carries one
+    (Z[:P][M[:P]].sum() + Z[P:][M[P:]].sum()).backward()
+    g_pair = lat.grad.clone()
+    lat.grad = None
+    a[0][a[1]].sum().backward()
+    assert gu.rel(g_pair, lat.grad) < 1e-5
+    n3 = lib.dist_launch_count()
+    out = rw.render_warp(lat, R1, T1, R2, T2, img1.cuda(), img2.cuda())
+    assert lib.dist_launch_count() - n3 < 0.75 * (n1 - n0) and out[3].dtype == torch.uint8
+
+
 def test_sdf_grid_matches_oracle():
     """next-2: device-resident dense / coarse-to-fine SDF grid (create_mesh.py sampling half) vs the pinned oracle."""
     import importlib
