@@ -105,6 +105,22 @@ def load_deepsdf():
     return _loaded["D"]
 
 
+def load_loss_single():
+    """The reference's compute_all_loss (core/inv_optimizer/loss_single.py) with its loss_utils patched for CPU uint8 masks."""
+    if "LS" in _loaded:
+        return _loaded["LS"]
+    load()
+    up = os.path.join(REF, "core", "utils")
+    if up not in sys.path:
+        sys.path.append(up)                          # loss_utils.py:7 `from pytorch_ssim import loss_ssim`
+    if "core.utils.loss_utils" not in sys.modules or not hasattr(sys.modules["core.utils.loss_utils"], "compute_loss_mask"):
+        _load("core.utils.loss_utils", "core/utils/loss_utils.py")
+    _stub("core.inv_optimizer", "/core/inv_optimizer")
+    LS = _load("core.inv_optimizer.loss_single", "core/inv_optimizer/loss_single.py")
+    _loaded["LS"] = LS.compute_all_loss
+    return _loaded["LS"]
+
+
 def load_create_mesh():
     """The reference's core/evaluation/create_mesh.py with skimage / plyfile stubbed (absent here; only the sampling
     half is exercised), `.cuda()` / `.cpu()` round trips neutralised and the torch>=1.6 true-division of

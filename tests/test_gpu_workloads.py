@@ -94,6 +94,33 @@ def test_inverse_optimisation_tracks_oracle():
     assert l_long[-1] < 0.9 * l_long[0]                            # the optimisation makes progress
 
 
+def test_compute_all_loss_on_product_outputs():
+    """the reference's single-view loss (compute_all_loss, loss_single.py:7-57, restated in
+    oracle/loss_oracle.py and pinned to the reference on CPU) consumes the product's outputs as they are -- uint8
+    silhouette, 1e11 background depth, zero background normals -- and its value / gradient agree with the CPU oracle's
+    renderer under the same loss.  Default march of compute_all_loss: pyramid_recursive."""
+    from oracle import loss_oracle
+    hw = (40, 40)
+    K, (R, T) = synth.intrinsic(*hw), synth.lookat_camera(30.0, 20.0, 1.8)
+    dec_c, dec_g = cases.decoder("B"), gu.gpu_decoder("B")
+    ora = OracleSDFRenderer(dec_c, K, img_hw=hw, march_step=60, buffer_size=3)
+    gt = ora.render(synth.make_latent(seed=2), R, T, no_grad=True)
+    gt_pack = {"depth": gt[0].detach(), "normal": gt[1].detach(), "silhouette": gt[2].detach()}
+    ext = torch.cat([R, T[:, None]], 1)
+    ren = pkg.SDFRenderer(dec_g, K, img_hw=hw, march_step=60, buffer_size=3)
+    for kind in ("pyramid_recursive", "recursive"):
+        l_c = synth.make_latent().requires_grad_(True)
+        pack_c = loss_oracle.compute_all_loss(ora, l_c, ext, gt_pack, ray_marching_type=kind)
+        loss_oracle.total(pack_c).backward()
+        l_g = synth.make_latent().cuda().requires_grad_(True)
+        pack_g = loss_oracle.compute_all_loss(ren, l_g, ext.cuda(), {k: v.cuda() for k, v in gt_pack.items()},
+                                              ray_marching_type=kind)
+        loss_oracle.total(pack_g).backward()
+        for k in ("mask_gt", "mask_out", "depth", "normal", "l2reg"):
+            assert abs(float(pack_g[k]) - float(pack_c[k])) <= 2e-3 * abs(float(pack_c[k])) + 1e-6, (kind, k)
+        assert gu.rel(l_g.grad.cpu(), l_c.grad) < 5e-3, kind
+
+
 def test_multi_view_ring_gradients():
     """Config 4 layout: views on a ring, summed loss, ONE backward over the shared code; vs the oracle on 3 views."""
     hw = (24, 24)

@@ -1,12 +1,14 @@
 """CPU: pin oracle/sdf_oracle.py against (a) golden fixtures written from the real reference and
 (b) the real reference itself where /root/reference is present (the build container)."""
 import os
+import sys
 
 import numpy as np
 import pytest
 import torch
 
 import cases
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
 from oracle import ref_shim
 from oracle.sdf_oracle import OracleSDFRenderer, decode_sdf, decode_sdf_gradient
 
@@ -86,6 +88,37 @@ def test_oracle_earlybreak_padding_render_depth(name):
     assert _rel(Zd.detach().numpy(), gold["rd_Zdepth"]) < 1e-6
     for g, key in zip((lat.grad, Rg.grad, Tg.grad), ("rd_g_latent", "rd_g_R", "rd_g_T")):
         assert _rel(g.numpy(), gold[key]) < 1e-4, key
+
+
+def _loss_setup(hw=(40, 40)):
+    K, (R, T) = cases.synth.intrinsic(*hw), cases.synth.lookat_camera(30.0, 20.0, 1.8)
+    ora = OracleSDFRenderer(cases.decoder("B"), K, img_hw=hw, march_step=60, buffer_size=3)
+    gt = ora.render(cases.synth.make_latent(seed=2), R, T, no_grad=True)
+    gt_pack = {"depth": gt[0].detach(), "normal": gt[1].detach(), "silhouette": gt[2].detach()}
+    return hw, K, R, T, ora, gt_pack
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="reference tree not present (GPU box)")
+def test_loss_oracle_matches_live_reference():
+    """oracle/loss_oracle.py == the reference's compute_all_loss (loss_single.py:7-57) on the reference's renderer:
+    every term of the loss pack, the weighted total and its gradient w.r.t. the shape code."""
+    from oracle import loss_oracle
+    import make_golden
+    hw, K, R, T, ora, gt_pack = _loss_setup()
+    Rmod, _, _ = ref_shim.load()
+    ref_loss = ref_shim.load_loss_single()
+    ren = Rmod.SDFRenderer(make_golden.ref_decoder(cases.decoder("B")), K, img_hw=hw, march_step=60, buffer_size=3, use_gpu=False)
+    ext = torch.cat([R, T[:, None]], 1)
+    l_r = cases.synth.make_latent().requires_grad_(True)
+    pack_r, _ = ref_loss(ren, l_r, ext, gt_pack, ray_marching_type='recursive')
+    loss_oracle.total(pack_r).backward()
+    l_o = cases.synth.make_latent().requires_grad_(True)
+    pack_o = loss_oracle.compute_all_loss(ora, l_o, ext, gt_pack, ray_marching_type='recursive')
+    loss_oracle.total(pack_o).backward()
+    for k in ("mask_gt", "mask_out", "depth", "normal", "l2reg"):
+        assert abs(float(pack_o[k]) - float(pack_r[k])) <= 1e-6 * max(1.0, abs(float(pack_r[k]))), k
+    assert float(pack_r["depth"]) > 0 and float(pack_r["normal"]) < 0
+    assert _rel(l_o.grad.numpy(), l_r.grad.numpy()) < 1e-5
 
 
 def test_big_fixtures_present_and_consistent():
