@@ -82,6 +82,9 @@ PROTOTYPES = {
                                          C.c_void_p, C.c_void_p, C.c_void_p]),
     "dist_render_depth_bwd": (C.c_int, [C.POINTER(Net), C.c_int, C.POINTER(Camera), C.POINTER(March),
                                         C.POINTER(Workspace)] + [C.c_void_p] * 15),
+    "dist_warp_loss_fwd": (C.c_int, [C.POINTER(Camera), C.POINTER(C.c_float)] + [C.c_void_p] * 7 + [C.c_float] +
+                           [C.c_void_p] * 6),
+    "dist_warp_loss_bwd": (C.c_int, [C.POINTER(Camera), C.POINTER(C.c_float)] + [C.c_void_p] * 13),
 }
 
 _lib = None

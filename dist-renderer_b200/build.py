@@ -12,7 +12,7 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"] + \
     os.environ.get("DIST_EXTRA_NVCC_FLAGS", "").split()      # e.g. -DDIST_TC_TIMELINE for the per-layer timeline of mlp_tc.cu
 # march.cu mirrors PyTorch's separately-rounded elementwise ops: no FMA contraction there
-SOURCES = {"abi.cu": [], "march.cu": ["-fmad=false"], "mlp_simt.cu": ["-Xptxas", "-v"], "mlp_tc.cu": ["-Xptxas", "-v"]}
+SOURCES = {"abi.cu": [], "warp.cu": [], "march.cu": ["-fmad=false"], "mlp_simt.cu": ["-Xptxas", "-v"], "mlp_tc.cu": ["-Xptxas", "-v"]}
 
 
 def _stamp():

@@ -3,19 +3,79 @@
 Drop-in for `core/sdfrenderer/renderer_warp.py:13-144`: view 1 is rendered with depth
 gradients, view 2 without; the hit points of view 1 are reprojected into view 2, filtered by a depth-consistency test
 against view 2's rendered depth, and the colours of both images are compared at the corresponding pixels (L1).
-All decoder work (ONE two-view march + one `render_normal`) runs on the engines of `renderer.SDFRenderer`;
-the reprojection / bilinear sampling is a handful of elementwise PyTorch ops on (3, N) tensors and stays in PyTorch,
-exactly as in the reference, so the loss carries gradients to `latent`, `R1`, `T1`.
+All decoder work (ONE two-view march + one `render_normal`) runs on the engines of `renderer.SDFRenderer`; the
+reprojection, the depth-consistency test, the bilinear sampling and the L1 loss are ONE kernel forward and one backward
+(`dist_warp_loss_fwd / _bwd`, csrc/warp.cu) instead of a dozen elementwise PyTorch ops on compacted (3, N) tensors with
+their boolean-mask host synchronisations; the loss carries gradients to `latent` (through view 1's depth), `R1`, `T1`,
+`R2`, `T2` as in the reference.  The PyTorch formulation (`get_valid_points`, `compute_loss_color`) is kept as methods with
+the reference's signatures for subclasses / callers that use them directly.
 
 `grid_sample` is called with ``align_corners=True``: the reference was written for torch 1.1, whose default sampling
 convention that is; the pixel normalisation `2 x / (W - 1) - 1` of `loss_utils.py:19-21`
 only makes sense under it.
 """
+import ctypes
+
 import numpy as np
 import torch
 import torch.nn.functional as F
 
-from .renderer import SDFRenderer
+from . import _abi
+from .renderer import SDFRenderer, _stream
+
+
+class _WarpLossFn(torch.autograd.Function):
+    """Sum of |img1 - sample(img2)| over the view-1 hit pixels whose reprojection into view 2 passes the depth test
+    (renderer_warp.py:18-101), and the number of such pixels."""
+
+    @staticmethod
+    def forward(ctx, Zdepth1, R1, T1, R2, T2, ren, mask1, depth2, img1, img2, thres):
+        with torch.cuda.device(ren.device):
+            lib, st, dev, P = _abi.lib(), _stream(ren.device), ren.device, ren.P
+            R1d, T1d = R1.detach().float().contiguous(), T1.detach().float().contiguous()
+            R2d, T2d = R2.detach().float().contiguous(), T2.detach().float().contiguous()
+            c1 = ren.get_camera_location(R1d, T1d).contiguous()
+            cam = ren._c_camera(R1d, c1)
+            K_host = (ctypes.c_float * 9)(*[float(v) for v in ren.intrinsic.reshape(-1)])
+            Z1 = Zdepth1.detach().float().contiguous()
+            m1 = mask1.to(torch.uint8).contiguous()
+            loss_sum = torch.empty(1, device=dev)
+            count = torch.empty(1, device=dev, dtype=torch.int32)
+            keep = torch.empty(P, device=dev, dtype=torch.uint8)
+            vis1, vis2 = torch.empty(P, 3, device=dev), torch.empty(P, 3, device=dev)
+            _abi.check(lib.dist_warp_loss_fwd(cam, K_host, _abi.ptr(R2d), _abi.ptr(T2d), _abi.ptr(Z1), _abi.ptr(m1),
+                                              _abi.ptr(depth2), _abi.ptr(img1), _abi.ptr(img2), float(thres),
+                                              _abi.ptr(loss_sum), _abi.ptr(count), _abi.ptr(keep), _abi.ptr(vis1),
+                                              _abi.ptr(vis2), st))
+            ctx.ren = ren
+            ctx.save_for_backward(Z1, R1d, T1d, R2d, T2d, keep, img1, img2)
+            ctx.mark_non_differentiable(count, keep, vis1, vis2)
+            return loss_sum, count, keep, vis1, vis2
+
+    @staticmethod
+    def backward(ctx, g, *_):
+        Z1, R1d, T1d, R2d, T2d, keep, img1, img2 = ctx.saved_tensors
+        ren = ctx.ren
+        with torch.cuda.device(ren.device):
+            lib, st, dev, P = _abi.lib(), _stream(ren.device), ren.device, ren.P
+            c1 = ren.get_camera_location(R1d, T1d).contiguous()
+            cam = ren._c_camera(R1d, c1)
+            K_host = (ctypes.c_float * 9)(*[float(v) for v in ren.intrinsic.reshape(-1)])
+            gs = g.detach().reshape(1).float().contiguous()
+            dZ1, d_ray = torch.empty(P, device=dev), torch.empty(3, P, device=dev)
+            d_c1, dR2, dT2 = torch.empty(3, device=dev), torch.empty(9, device=dev), torch.empty(3, device=dev)
+            _abi.check(lib.dist_warp_loss_bwd(cam, K_host, _abi.ptr(R2d), _abi.ptr(T2d), _abi.ptr(Z1), _abi.ptr(keep),
+                                              _abi.ptr(img1), _abi.ptr(img2), _abi.ptr(gs), _abi.ptr(dZ1), _abi.ptr(d_ray),
+                                              _abi.ptr(d_c1), _abi.ptr(dR2), _abi.ptr(dT2), st))
+            gR1 = gT1 = None
+            if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+                with torch.enable_grad():       # c1 = -R1^T T1, ray = normalize(R1^T K^-1 u): 12-float Jacobian on the host
+                    Rg, Tg = R1d.clone().requires_grad_(True), T1d.clone().requires_grad_(True)
+                    gR1, gT1 = torch.autograd.grad([ren.get_camera_location(Rg, Tg), ren.get_camera_rays(Rg)], [Rg, Tg],
+                                                   [d_c1, d_ray], allow_unused=True)
+            return (dZ1 if ctx.needs_input_grad[0] else None, gR1, gT1,
+                    dR2.reshape(3, 3) if ctx.needs_input_grad[3] else None, dT2 if ctx.needs_input_grad[4] else None,
+                    None, None, None, None, None, None)
 
 
 def grid_sample_on_img(img, xy):
@@ -97,8 +157,14 @@ class SDFRenderer_warp(SDFRenderer):
             vis1 = torch.zeros_like(img1).to(self.device)
             vis2 = torch.zeros_like(img1).to(self.device)
         else:
-            xy, km, kd = self.get_valid_points(out1, out2, R1, T1, R2, T2, thres_depth)
-            loss_color, vis1, vis2 = self.compute_loss_color(img1, img2, xy, valid_mask1, km, kd)
+            # renderer_warp.py:125-127 (get_valid_points + compute_loss_color): one fused kernel
+            depth2 = (Zdepth2.detach() * self.calib_map).contiguous()
+            i1 = img1.to(self.device).float().reshape(P, 3).contiguous()
+            i2 = img2.to(self.device).float().reshape(P, 3).contiguous()
+            loss_sum, count, _keep, v1, v2 = _WarpLossFn.apply(Zdepth1, R1, T1, R2, T2, self, valid_mask1, depth2, i1, i2,
+                                                               float(thres_depth))
+            loss_color = (loss_sum / (3.0 * count.float())).reshape(())      # mean over (n, 3); NaN when nothing is kept
+            vis1, vis2 = v1.reshape(h, w, 3).to(img1.dtype), v2.reshape(h, w, 3).to(img1.dtype)
         normal1 = self.render_normal(latent, R1, T1, Zdepth1, valid_mask1, no_grad=no_grad_normal, clamp_dist=clamp_dist)
         Zn = torch.matmul(R1, normal1)
         Zn = torch.cat([Zn[:1] * (-1), Zn[1:]], 0).reshape(3, h, w).permute(1, 2, 0)

@@ -261,6 +261,25 @@ int dist_render_depth_bwd(const dist_net_t* net, int engine, const dist_camera_t
                           float* scratch_coef, uint8_t* scratch_clamp, float* scratch_dpts, int32_t* scratch_count,
                           int64_t* rows_evaluated, void* stream);
 
+/* ---- two-view photometric warp (renderer_warp.py:18-101, loss_utils.py:9-25) ---- */
+
+/* For every pixel of view 1 with mask1 != 0: p = cam_pos1 + ray1 * Zdepth1 (world frame), xyz = K (R2 p + T2), (u, v) =
+ * xyz.xy / xyz.z; the pixel is kept when (xyz.z - bilinear(depth2, u, v))^2 < thres_depth (depth2: view 2's z-depth map,
+ * [P]); for kept pixels the colour of img1 [P][3] is compared with the bilinear sample of img2 [P][3] at (u, v)
+ * (torch-1.1 grid_sample convention: align_corners=True, zero padding).  Outputs: loss_sum[1] = sum of |c1 - c2| over kept
+ * pixels and channels, count[1] = kept pixels (the reference's loss is loss_sum / (3 count)), keep[P], vis1 / vis2 [P][3]
+ * (the two colours at kept pixels, zero elsewhere).  cam1: view 1 (full image, one view); K_host: intrinsic, HOST [9];
+ * R2, T2: device.  Replaces get_valid_points / valid_points_depth / compute_loss_color + grid_sample_on_img. */
+int dist_warp_loss_fwd(const dist_camera_t* cam1, const float* K_host, const float* R2, const float* T2, const float* Zdepth1,
+                       const uint8_t* mask1, const float* depth2, const float* img1, const float* img2, float thres_depth,
+                       float* loss_sum, int32_t* count, uint8_t* keep, float* vis1, float* vis2, void* stream);
+
+/* Backward of dist_warp_loss_fwd for gscale[0] = dL/d(loss_sum) (device): dZdepth1[P], d_ray1[3][P] (w.r.t. view 1's unit
+ * rays), d_cam_pos1[3], dR2[9], dT2[3].  The depth-consistency test and the images carry no gradient, as in the reference. */
+int dist_warp_loss_bwd(const dist_camera_t* cam1, const float* K_host, const float* R2, const float* T2, const float* Zdepth1,
+                       const uint8_t* keep, const float* img1, const float* img2, const float* gscale, float* dZdepth1,
+                       float* d_ray1, float* d_cam_pos1, float* dR2, float* dT2, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -304,6 +304,34 @@ def test_render_warp_marches_both_views_together():
     assert lib.dist_launch_count() - n3 < 0.75 * (n1 - n0) and out[3].dtype == torch.uint8
 
 
+def test_fused_warp_loss_equals_the_pytorch_formulation():
+    """next-1, second half: dist_warp_loss_fwd/_bwd (reprojection + depth test + bilinear sampling + L1 in one kernel)
+    against the reference's formulation in PyTorch ops (get_valid_points / compute_loss_color, kept as methods): loss,
+    the two visualisation maps, and the gradients w.r.t. latent, R1, T1, R2, T2."""
+    import importlib
+    warp = importlib.import_module("dist-renderer_b200.renderer_warp")
+    hw, K, (R1, T1), (R2, T2), img1, img2 = cases.warp_case()
+    rw = warp.SDFRenderer_warp(gu.gpu_decoder("B"), K, img_hw=hw)
+    img1, img2 = img1.cuda(), img2.cuda()
+
+    def leaves():
+        return [t.cuda().clone().requires_grad_(True) for t in (synth.make_latent(), R1, T1, R2, T2)]
+    a = leaves()
+    out = rw.render_warp(a[0], a[1], a[2], a[3], a[4], img1, img2)
+    out[0].backward()
+    b = leaves()
+    o1 = rw.render_depth(b[0], b[1], b[2])
+    o2 = rw.render_depth(b[0], b[3], b[4], no_grad_depth=True)
+    xy, km, kd = rw.get_valid_points(o1, o2, b[1], b[2], b[3], b[4], 0.001)
+    loss, v1, v2 = rw.compute_loss_color(img1, img2, xy, o1[1], km, kd)
+    loss.backward()
+    assert int(kd.sum()) > 50
+    assert abs(float(out[0]) - float(loss)) < 1e-5 * abs(float(loss))
+    assert gu.rel(out[1], v1) < 1e-6 and gu.rel(out[2], v2) < 1e-5
+    for name, x, y in zip(("latent", "R1", "T1", "R2", "T2"), a, b):
+        assert y.grad is not None and gu.rel(x.grad, y.grad) < 2e-3, (name, gu.rel(x.grad, y.grad))
+
+
 def test_sdf_grid_matches_oracle():
     """next-2: device-resident dense / coarse-to-fine SDF grid (create_mesh.py sampling half) vs the pinned oracle."""
     import importlib
