@@ -39,19 +39,26 @@ def _check_points(points):
 
 
 class _DecodeFn(torch.autograd.Function):
+    """Decoder rows on the CUDA engines, (K, n_out).  The kernels compute one output per launch: a multi-output network
+    (the colour decoder) is evaluated output by output, every hidden layer shared (plan.c_net(out_index=...))."""
+
     @staticmethod
     def forward(ctx, latent, points, plan, clamp_dist, engine):
         lib = _abi.lib()
         _check_device(plan, points)
         with torch.cuda.device(plan.device):
             st = _stream(plan.device)
-            net, engine, _keep = plan.net_for(latent, engine, st)
             pts = points.detach().float().contiguous()
             n = pts.shape[0]
-            sdf = torch.empty(n, 1, device=pts.device, dtype=torch.float32)
+            cols = []
             cd = float(clamp_dist) if clamp_dist is not None else 0.0
-            if n > 0:
-                _abi.check(lib.dist_decoder_forward(net, engine, _abi.ptr(pts), n, None, cd, _abi.ptr(sdf), st))
+            for c in range(plan.n_out):
+                net, engine, _keep = plan.net_for(latent, engine, st, out_index=c)
+                out = torch.empty(n, device=pts.device, dtype=torch.float32)
+                if n > 0:
+                    _abi.check(lib.dist_decoder_forward(net, engine, _abi.ptr(pts), n, None, cd, _abi.ptr(out), st))
+                cols.append(out)
+            sdf = torch.stack(cols, 1) if plan.n_out > 1 else cols[0].reshape(n, 1)
         ctx.plan, ctx.cd, ctx.engine = plan, cd, engine
         ctx.save_for_backward(pts, latent if latent is not None else torch.empty(0, device=pts.device))
         ctx.has_latent = latent is not None
@@ -63,15 +70,19 @@ class _DecodeFn(torch.autograd.Function):
         plan, lib = ctx.plan, _abi.lib()
         with torch.cuda.device(plan.device):
             st = _stream(plan.device)
-            net, eng_b, _keep = plan.net_for(latent if ctx.has_latent else None, ctx.engine, st)
             n = pts.shape[0]
-            coef = g.detach().reshape(-1).float().contiguous()
             dpts = torch.zeros(n, 3, device=pts.device)
             acc0 = torch.zeros(plan.bias[0].numel(), device=pts.device)
             accl = torch.zeros(plan.bias[plan.latent_in].numel(), device=pts.device) if plan.latent_in >= 0 else None
-            if n > 0:
-                _abi.check(lib.dist_decoder_backward(net, eng_b, _abi.ptr(pts), _abi.ptr(coef), None, n, None, ctx.cd,
-                                                     _abi.ptr(dpts), _abi.ptr(acc0), _abi.ptr(accl), st))
+            gd = g.detach().float()
+            for c in range(plan.n_out):
+                net, eng_b, _keep = plan.net_for(latent if ctx.has_latent else None, ctx.engine, st, out_index=c)
+                coef = gd[:, c].contiguous()
+                dp = torch.empty(n, 3, device=pts.device)
+                if n > 0:
+                    _abi.check(lib.dist_decoder_backward(net, eng_b, _abi.ptr(pts), _abi.ptr(coef), None, n, None, ctx.cd,
+                                                         _abi.ptr(dp), _abi.ptr(acc0), _abi.ptr(accl), st))
+                    dpts += dp
         g_lat = plan.latent_grad(acc0, accl).reshape(latent.shape) if (ctx.has_latent and ctx.needs_input_grad[0]) \
             else None
         return g_lat, (dpts if ctx.needs_input_grad[1] else None), None, None, None
@@ -85,6 +96,8 @@ def decode_sdf(decoder, latent_vector, points, clamp_dist=0.1, MAX_POINTS=100000
     """
     _check_points(points)
     plan = plan_for(decoder)
+    if plan.n_out != 1:
+        raise ValueError("decode_sdf expects a single-output decoder (use decode_color for the colour network)")
     eng = resolve_engine(plan, engine or DEFAULT_ENGINE)
     if no_grad:
         with torch.no_grad():
@@ -118,19 +131,22 @@ def decode_sdf_gradient(decoder, latent_vector, points, clamp_dist=0.1, MAX_POIN
     return grad
 
 
-def decode_color(decoder, color_code, shape_code, points, MAX_POINTS=100000, no_grad=False):
+def decode_color(decoder, color_code, shape_code, points, MAX_POINTS=100000, no_grad=False, engine=None):
     """rgb (K,3) of `points` (K,3) from a colour decoder fed [shape code | colour code | xyz] rows --
     decoder_utils.py:94-112 (used by SDFRenderer_color, renderer_rgb.py:33).
 
-    The colour network (``last_dim = 3``) is evaluated once per hit pixel after the march (about 1e-3 of the decoder
-    rows of a render), through the module's generic PyTorch layers: the fused engines cover the single-output SDF
-    network.  Rows go through in chunks of MAX_POINTS like upstream, so the GEMM shapes -- and with them the last bits
-    of the result -- are the reference's."""
-    n = points.shape[0]
-    chunks = []
-    for start in range(0, max(n, 1), MAX_POINTS):
-        end = min(start + MAX_POINTS, n)
-        inputs = torch.cat([shape_code.expand(end - start, -1), color_code.expand(end - start, -1), points[start:end]], 1)
-        color = decoder.inference(inputs)
-        chunks.append(color.detach() if no_grad else color)
-    return torch.cat(chunks, 0)
+    The colour network (``last_dim = 3``, latent = shape code + colour code) runs on the same fused engines as the SDF
+    network: both codes are folded into the per-render biases, the hidden layers run on tcgen05 (or exact fp32), and the
+    three outputs are three dot-product epilogues over the shared hidden layers (three launches of the single-output
+    kernel; a render queries the colour network once per hit pixel, ~1e-3 of its decoder rows).  Differentiable w.r.t.
+    both codes and the points.  MAX_POINTS is accepted for signature compatibility (no host-side chunking needed)."""
+    _check_points(points)
+    plan = plan_for(decoder)
+    if plan.n_out != 3:
+        raise ValueError("decode_color expects a decoder with three outputs (last_dim=3)")
+    eng = resolve_engine(plan, engine or DEFAULT_ENGINE)
+    latent = torch.cat([shape_code.reshape(1, -1), color_code.reshape(1, -1)], 1)      # decoder_utils.py:103
+    if no_grad:
+        with torch.no_grad():
+            return _DecodeFn.apply(latent, points, plan, None, eng)
+    return _DecodeFn.apply(latent, points, plan, None, eng)

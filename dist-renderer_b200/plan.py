@@ -105,8 +105,12 @@ class DecoderPlan(object):
             self.K.append(k); self.N.append(n_out)
             self.Wt.append(wt); self.W.append(wn); self.bias.append(bp)
             prev = n_out
-        if self.N[-1] != 1:
-            raise NotImplementedError("last_dim != 1 decoders (colour) are not supported by the fused path")
+        # The kernels evaluate ONE output per launch (dot product + tanh in the epilogue).  A decoder with several outputs
+        # (the colour network of renderer_rgb.py:20-38, last_dim = 3) is evaluated as n_out single-output networks that
+        # share every hidden layer: c_net(out_index=c) points the last layer at row c of its weights.
+        self.n_out = self.N[-1]
+        if self.n_out > 4:
+            raise NotImplementedError("decoders with more than 4 outputs are not supported by the fused path")
         self.use_tanh = 1 if getattr(d, "use_tanh", False) else 0
         self.tc = None      # tensor-core operand blobs, built lazily by tc.prepare()
         self.tc_unsafe = False
@@ -129,9 +133,9 @@ class DecoderPlan(object):
         _abi.check(lib.dist_fold_latent(net, _abi.ptr(lat), _abi.ptr(out0), _abi.ptr(outl), stream))
         return out0, outl, lat
 
-    def net_for(self, latent, engine, stream):
+    def net_for(self, latent, engine, stream, out_index=0):
         """(dist_net_t, effective engine, keepalive) for one call: prepares the tensor-core operands when that engine is selected,
-        folds the latent into the per-render biases and fills the descriptor."""
+        folds the latent into the per-render biases and fills the descriptor (for output `out_index` of the network)."""
         if engine == _abi.ENGINE_TC:
             from . import tc
             try:
@@ -145,11 +149,14 @@ class DecoderPlan(object):
         if engine == _abi.ENGINE_TC and bl is not None:
             from . import tc
             bl_tc = bl * tc.S_ACT
-        net = self.c_net(b0, bl, bl_tc)
+        net = self.c_net(b0, bl, bl_tc, out_index=out_index)
         return net, engine, (b0, bl, bl_tc, lat)
 
-    def c_net(self, bias0, biasl, biasl_tc=None):
-        """ctypes dist_net_t for one call; bias0/biasl are the folded biases (or None before folding)."""
+    def c_net(self, bias0, biasl, biasl_tc=None, out_index=0):
+        """ctypes dist_net_t for one call; bias0/biasl are the folded biases (or None before folding); `out_index` selects
+        which output of a multi-output network the (single-output) kernels compute."""
+        if not (0 <= out_index < self.n_out):
+            raise ValueError("out_index %d outside the decoder's %d outputs" % (out_index, self.n_out))
         net = _abi.Net()
         net.n_layers, net.latent_size, net.latent_in, net.use_tanh = self.n_layers, self.latent_size, \
             self.latent_in, self.use_tanh
@@ -162,6 +169,10 @@ class DecoderPlan(object):
             if l == self.latent_in and biasl is not None:
                 b = biasl
             net.bias[l] = b.data_ptr()
+        last = self.n_layers - 1
+        net.N[last] = 1
+        net.W[last] = self.W[last].data_ptr() + 4 * out_index * self.W[last].shape[1]      # row out_index of [Np8][Kp4]
+        net.bias[last] = self.bias[last].data_ptr() + 4 * out_index
         net.Wz0 = self.Wz0.data_ptr() if self.Wz0 is not None and self.Wz0.numel() else None
         net.b0 = self.b0.data_ptr()
         if self.latent_in >= 0:

@@ -2,10 +2,10 @@
 
 Drop-in for `core/sdfrenderer/renderer_rgb.py:12-125` (the demo path): depth, normal and
 silhouette come from `renderer.SDFRenderer` (tensor-core march, fused analytic normals); the colour network -- a
-DeepSDF-style MLP with three outputs fed [shape code | colour code | xyz] -- is queried ONCE per hit pixel, and the
-optional point-light shading is a few elementwise ops on the hit pixels.  Those two stay in PyTorch exactly as in the
-reference (`functional.decode_color` explains why: ~1e-3 of the decoder rows of a render, and a three-output last
-layer the single-output engines do not cover), so the colour carries gradients to both codes as upstream.
+DeepSDF-style MLP with three outputs fed [shape code | colour code | xyz] -- is queried ONCE per hit pixel on the same
+fused engines (`functional.decode_color`: both codes folded into the per-render biases, hidden layers shared, three
+dot-product epilogues), and the optional point-light shading is a few elementwise ops on the hit pixels.  The colour
+carries gradients to both codes as upstream.
 """
 import torch
 
@@ -33,7 +33,8 @@ class SDFRenderer_color(SDFRenderer):
             # upstream returns the empty canvas reshaped to (3, H*W) here (renderer_rgb.py:27-28); kept as is
             return torch.zeros(3, h * w, device=self.device, dtype=torch.float32)
         points = self.generate_point_samples(cam_pos, cam_rays[:, idx], Zdepth[idx], has_zdepth_grad=False)
-        rgb = decode_color(self.decoder_color, latent_color, latent, points.transpose(1, 0), no_grad=no_grad)
+        rgb = decode_color(self.decoder_color, latent_color, latent, points.transpose(1, 0), no_grad=no_grad,
+                           engine=self.engine)
         color = torch.zeros(h * w, 3, device=self.device, dtype=rgb.dtype).index_copy(0, idx, rgb).reshape(h, w, 3)
         return color.detach() if no_grad else color
 

@@ -58,6 +58,78 @@ def test_decode_sdf_autograd(engine):
     assert gu.rel(p_g.grad, p_c.grad) < 1e-4
 
 
+def test_tc_operand_range_margin_and_fallback():
+    """The split-fp16 operands carry activations in units of 32, i.e. up to ~2000 before fp16 overflows.  Scale the
+    weight-norm gains of the synthetic decoder so that its hidden activations reach trained-network magnitudes (1e2..1e3)
+    and beyond: within the range the tensor-core engine stays at fp32 noise from the exact engine; beyond it, the
+    prepare-time self-check disables it LOUDLY (warning; 'auto' resolves to the fp32 engine, engine='tc' raises) instead of
+    returning non-finite values.  Prints the margin table."""
+    import copy
+    import warnings
+    g = torch.Generator().manual_seed(2)
+    pts = ((torch.rand(20000, 3, generator=g) - 0.5) * 1.6).cuda()
+    lat = cases.synth.make_latent().cuda()
+    rows = []
+    for gain in (1.0, 1.6, 2.2, 2.6, 3.2):
+        dec = copy.deepcopy(cases.decoder("B")).cuda()
+        with torch.no_grad():
+            for l in range(1, 8):
+                getattr(dec, "lin%d" % l).weight_g.mul_(gain)
+        acts = []
+        hooks = [getattr(dec, "lin%d" % l).register_forward_hook(lambda m, i, o: acts.append(float(o.abs().max()))) for l in range(8)]
+        with torch.no_grad():
+            dec._inference_torch(torch.cat([lat.expand(4096, -1), pts[:4096]], 1))
+        for h in hooks:
+            h.remove()
+        amax = max(acts)
+        ref = pkg.decode_sdf(dec, lat, pts, clamp_dist=None, no_grad=True, engine="simt")
+        with warnings.catch_warnings(record=True) as wlist:
+            warnings.simplefilter("always")
+            try:
+                out = pkg.decode_sdf(dec, lat, pts, clamp_dist=None, no_grad=True, engine="tc")
+                err, state = float((out - ref).abs().max()), "tc"
+            except NotImplementedError:
+                err, state = float("nan"), "tc refused"
+            auto = pkg.decode_sdf(dec, lat, pts, clamp_dist=None, no_grad=True, engine="auto")
+        assert bool(torch.isfinite(auto).all()) and float((auto - ref).abs().max()) < 5e-5       # 'auto' is always safe
+        rows.append((gain, amax, state, err, len(wlist)))
+        if amax < 1500.0:
+            assert state == "tc" and err < 2e-5, rows[-1]
+        if state == "tc refused":
+            assert len(wlist) >= 1 and amax > 1500.0, rows[-1]
+    print("\n gain  max|activation|  engine      max|tc - fp32|  warnings")
+    for r in rows:
+        print(" %4.1f  %14.1f  %-10s  %14.3g  %d" % r)
+    assert any(r[1] > 100.0 and r[2] == "tc" for r in rows)          # trained-network-like magnitudes are covered
+    assert any(r[2] == "tc refused" for r in rows)                   # and the overflow case is exercised
+
+
+@pytest.mark.parametrize("engine", ["simt", "tc"])
+def test_decode_color_runs_on_the_fused_engines(engine):
+    """next-3: the three-output colour network (decoder_utils.py:94-112) on the CUDA engines -- both codes folded into the
+    per-render biases, hidden layers shared, three dot-product epilogues -- against the module's eager PyTorch layers:
+    values and the gradients w.r.t. shape code, colour code and points; and it is the library that runs (launch count)."""
+    import copy
+    import importlib
+    lib = importlib.import_module("dist-renderer_b200._abi").lib()
+    col = copy.deepcopy(cases.synth.make_color_decoder()).cuda()
+    g = torch.Generator().manual_seed(21)
+    pts = ((torch.rand(700, 3, generator=g) - 0.5) * 1.2).cuda()
+    w = torch.randn(700, 3, generator=g).cuda()
+    shape0, cc0 = cases.synth.make_latent().cuda(), (0.1 * torch.randn(1, 8, generator=g)).cuda()
+    sa, ca, pa = shape0.clone().requires_grad_(True), cc0.clone().requires_grad_(True), pts.clone().requires_grad_(True)
+    pkg.decode_color(col, ca, sa, pa, engine=engine)          # engine preparation outside the counted region
+    n0 = lib.dist_launch_count()
+    rgb = pkg.decode_color(col, ca, sa, pa, engine=engine)
+    assert lib.dist_launch_count() - n0 >= 3 and rgb.shape == (700, 3)
+    (rgb * w).sum().backward()
+    sb, cb, pb = shape0.clone().requires_grad_(True), cc0.clone().requires_grad_(True), pts.clone().requires_grad_(True)
+    ref = col._inference_torch(torch.cat([sb.expand(700, -1), cb.expand(700, -1), pb], 1))
+    (ref * w).sum().backward()
+    assert gu.rel(rgb, ref) < 1e-5 and float((rgb - ref).abs().max()) < 5e-6
+    assert gu.rel(sa.grad, sb.grad) < 1e-4 and gu.rel(ca.grad, cb.grad) < 1e-4 and gu.rel(pa.grad, pb.grad) < 1e-4
+
+
 @pytest.mark.parametrize("engine", ["simt", "tc"])
 @pytest.mark.parametrize("name", RENDER_CASES)
 def test_render_matches_oracle(name, engine):
