@@ -18,6 +18,12 @@
 //   * accumulators ping-pong between two 256-column TMEM buffers; 16 epilogue warps own 32 rows x 32 columns each;
 //   * the transposed chain (input gradient / backward replay) is the same machinery on W^T tiles, with the ReLU sign
 //     bits kept per thread and the latent gradient accumulated as per-lane running column sums.
+//   * two precision tiers (MODE 0, round 2): rows of the first row segment -- rays the march predicts to stay beyond its
+//     clamp band -- are evaluated with ONE fp16 pass (A_hi W_hi, hi halves of the weight stages only), two tiles at a time
+//     ("pair mode": the second tile's activations occupy the lo region, its accumulators the second TMEM buffer, both tiles
+//     consume every weight stage); a half-tile keeps its one-pass values only if all of its rows come out beyond the band,
+//     otherwise the tile is recorded in a per-CTA bitmap and re-evaluated with the three passes in a second sweep over the
+//     cluster's tiles after one cluster barrier (the CTAs read each other's bitmap through distributed shared memory);
 // Warp roles per CTA (640 threads): warp 0 TMA producer, warp 1 MMA issuer (leader CTA), warp 2 TMEM allocator,
 // warps 4-19 epilogue (TMEM lane quarter = warp % 4, 32-column quarter = (warp-4)/4).
 // DIST_TC_DEBUG (env): bit 2 prints cycles/ns of CTA 0 (+ a per-layer timeline when compiled with -DDIST_TC_TIMELINE).
@@ -184,21 +190,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 }
 
 // Writes 8 consecutive features (one K-group panel row) of this thread's row: x[] already multiplied by sA.
-// with_lo = false (one-pass tiles): only the hi half is read by the MMAs, the lo half is left stale
-__device__ __forceinline__ void store_group(uint8_t* smem, int feat0, int row, const float* x, bool with_lo = true) {
+__device__ __forceinline__ void store_group(uint8_t* smem, int feat0, int row, const float* x) {
   __half2 h[4], l[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(x[2 * i], x[2 * i + 1]);
+  for (int i = 0; i < 4; ++i) {
+    h[i] = __floats2half2_rn(x[2 * i], x[2 * i + 1]);
+    const float2 hf = __half22float2(h[i]);
+    l[i] = __floats2half2_rn(x[2 * i] - hf.x, x[2 * i + 1] - hf.y);
+  }
   const int off = (feat0 >> 3) * 1024 + row * 16;
   *reinterpret_cast<uint4*>(smem + OFF_AHI + off) = *reinterpret_cast<uint4*>(h);
-  if (with_lo) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float2 hf = __half22float2(h[i]);
-      l[i] = __floats2half2_rn(x[2 * i] - hf.x, x[2 * i + 1] - hf.y);
-    }
-    *reinterpret_cast<uint4*>(smem + OFF_ALO + off) = *reinterpret_cast<uint4*>(l);
-  }
+  *reinterpret_cast<uint4*>(smem + OFF_ALO + off) = *reinterpret_cast<uint4*>(l);
 }
 
 // pair mode: hi halves only, into the activation region at byte offset `region` (OFF_AHI: tile 0, OFF_ALO: tile 1)
@@ -255,7 +257,6 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
   volatile uint32_t* fail_words = reinterpret_cast<volatile uint32_t*>(smem + OFF_FAIL + 16);
   const uint32_t fail_addr = sbase + OFF_FAIL + 16;
   auto tile_of = [&](int i) -> int64_t { return cluster_id + (int64_t)i * n_clusters; };
-  auto tile_exact = [&](int64_t t) -> bool { return !screening || t >= tiles1; };
   // One-pass tiles are processed TWO AT A TIME ("pair mode"): the second tile's activations live where a full-precision tile
   // keeps its lo halves (OFF_ALO), its accumulators in the second TMEM buffer, and both tiles consume every weight stage --
   // the weight stream and the barrier traffic are paid once per 256 rows, and the tensor pipe has the other tile's MMAs to
@@ -740,7 +741,6 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
         i = inext;
         continue;
       }
-      const bool exact = true;
       const int64_t gr = row0_of(t) + rank * 64 + row;
       const bool row_ok = gr < lim_of(t);
       float dot = 0.f, rowscale = 0.f, dx = 0.f, dy = 0.f, dz = 0.f;
@@ -842,7 +842,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
             } else if (need_store) {
               wait_free(kb);
 #pragma unroll
-              for (int g = 0; g < 4; ++g) store_group(smem, fb + 8 * g, row, &v[8 * g], exact);
+              for (int g = 0; g < 4; ++g) store_group(smem, fb + 8 * g, row, &v[8 * g]);
               signal_block(kb);
             }
           } else {
@@ -914,8 +914,6 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
             float oc = o;
             if (io.clamp_dist > 0.f) oc = fminf(fmaxf(o, -io.clamp_dist), io.clamp_dist);
             if (row_ok && io.sdf) io.sdf[gr] = oc;
-            // one-pass tile: a row that may be inside the clamp band (or is not a number) fails the half-tile
-            if (MODE == 0 && !exact && row_ok && !(fabsf(o) > io.screen_thresh)) *near_flag = 1u;
             if (MODE != 0) {
               float d = 1.f - o * o;
               if (P.use_tanh) d *= (1.f - t1 * t1);
@@ -929,14 +927,9 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
             }
           }
           epi_bar_sync();
-          if (MODE == 0 && ew == 0 && lane == 0) {
-            bool approx = false;
-            if (!exact) {
-              if (*near_flag) { fail_words[i >> 5] |= 1u << (i & 31); *near_flag = 0u; }   // redo in phase 1
-              else approx = true;
-            }
-            if (io.seg_approx && row0_of(t) + rank * 64 < lim_of(t)) io.seg_approx[(row0_of(t) >> 6) + rank] = approx ? 1 : 0;
-            if (exact) ++n_tiles_3pass; else ++n_tiles_1pass;
+          if (MODE == 0 && ew == 0 && lane == 0) {     // a single tile is always a full-precision tile (one-pass tiles: run_pair)
+            if (io.seg_approx && row0_of(t) + rank * 64 < lim_of(t)) io.seg_approx[(row0_of(t) >> 6) + rank] = 0;
+            ++n_tiles_3pass;
           }
           if (MODE != 0) {
             rowscale = rowd[row];

@@ -16,6 +16,8 @@ Differences from the reference, all loud:
     of image rows for ray-tile sharding across GPUs (parallel.py); ``render_views`` marches V poses of one shape in
     one fused call.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -213,7 +215,6 @@ class SDFRenderer(object):
         # 128-row tile programs of the forward launches evaluated with [one fp16 pass, three split-precision passes]
         self.tile_counters = torch.zeros(2, device=self.device, dtype=torch.int64)
         # two-tier precision of the march (dist_march_t.screen): on unless switched off here or by DIST_SCREEN=0
-        import os
         self.screen = (os.environ.get("DIST_SCREEN", "1") != "0") if screen is None else bool(screen)
         self.screen_tpred = float(os.environ.get("DIST_SCREEN_TPRED", screen_tpred))
         self.screen_ext_margin = float(os.environ.get("DIST_SCREEN_EXT", screen_ext_margin))
