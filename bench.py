@@ -344,7 +344,8 @@ def main():
     with ClockSampler(local_rank if not os.environ.get('BENCH_NO_SAMPLER') else -1) as clk:
         ms, step_ms = timed(lambda: step_device(lat_d, R_d, T_d), args.steps, 0)
     launches = lib.dist_launch_count() - l0
-    rows_f, rows_g = int(ren.local.rows_evaluated.item()), int(ren.local.rows_grad.item())
+    rows_f = int(ren.local.rows_evaluated.item())
+    rows_g, rows_gc = [int(v) for v in ren.local.rows_grad.tolist()]     # full gradient rows (2F), mask-cache replays (F)
     tiles_1p, tiles_3p = [int(v) / args.steps for v in ren.local.tile_counters.tolist()]
     value = side * side * args.steps / (ms * 1e-3)
     clocks = clk.summary()
@@ -372,7 +373,7 @@ def main():
     span = lambda a, b: sum(x.elapsed_time(y) for x, y in zip(ev[a], ev[b])) / n_prof
     prof = {"steps": n_prof, "step_ms": p0.elapsed_time(p1) / n_prof, "kernel_ms": k_total_ms.value / n_prof,
             "launches": k_launches.value / n_prof, "rows_f": int(ren.local.rows_evaluated.item()) / n_prof,
-            "rows_g": int(ren.local.rows_grad.item()) / n_prof,
+            "rows_g": int(ren.local.rows_grad[0].item()) / n_prof, "rows_gc": int(ren.local.rows_grad[1].item()) / n_prof,
             "tiles_1p": int(ren.local.tile_counters[0].item()) / n_prof, "tiles_3p": int(ren.local.tile_counters[1].item()) / n_prof,
             "pack_ms": span("pack0", "pack1"), "gather_ms": span("pack1", "gather1"), "unpack_ms": span("gather1", "unpack1")}
     keys = ("step_ms", "kernel_ms", "pack_ms", "gather_ms", "unpack_ms")
@@ -470,14 +471,15 @@ def main():
         torch.cuda.synchronize()
         k_ms = e0.elapsed_time(e1) / reps
         isolated = n_rows * F / (k_ms * 1e-3) / 1e12
-        in_step = (rows_f * F + rows_g * 2 * F) / (ms * 1e-3) / 1e12
-        # dominant kernel inside the step: useful flops of its launches / their summed event-timed durations
-        achieved = (prof["rows_f"] * F + prof["rows_g"] * 2 * F) / (prof["kernel_ms"] * 1e-3) / 1e12
+        in_step = (rows_f * F + rows_g * 2 * F + rows_gc * F) / (ms * 1e-3) / 1e12
+        # dominant kernel inside the step: useful flops of its launches / their summed event-timed durations.  A backward row
+        # replayed from the mask cache runs the transposed chain only: F, not 2F
+        achieved = (prof["rows_f"] * F + prof["rows_g"] * 2 * F + prof["rows_gc"] * F) / (prof["kernel_ms"] * 1e-3) / 1e12
         tc_on = ren.local.plan.tc is not None
         passes = 3 if tc_on else 1
         # MMA flops actually issued by the decoder kernels per step: forward tile programs (128 rows each, padding rows
         # included) with one or three fp16 passes, gradient rows (forward + transposed chain) always with three
-        issued = ((prof["tiles_1p"] + 3 * prof["tiles_3p"]) * 128 * F + prof["rows_g"] * 2 * 3 * F) if tc_on else \
+        issued = ((prof["tiles_1p"] + 3 * prof["tiles_3p"]) * 128 * F + (2 * prof["rows_g"] + prof["rows_gc"]) * 3 * F) if tc_on else \
             (prof["rows_f"] + 2 * prof["rows_g"]) * F
         issued_tf = issued / (prof["kernel_ms"] * 1e-3) / 1e12
         roof = {"bound": "tensor", "achieved": achieved, "peak": peak_sust, "unit": "TFLOP/s",
@@ -498,10 +500,12 @@ def main():
                              "burst_peak": peak_burst,
                              "note": "one 262,144-row forward launch at full split precision (3 fp16 MMA passes), after a cooldown"},
                 "traffic_note": "dram bytes of one 262,144-row launch with a dense march step's tier mix (ncu --set full, profiles/r2_tc_raw.csv)",
-                "note": "achieved counts USEFUL flops (F per folded decoder row, 2F per gradient row) over the event-timed "
+                "note": "achieved counts USEFUL flops (F per folded decoder row, 2F per gradient row, F per backward row replayed "
+                        "from the forward's ReLU-mask cache, which runs the transposed chain only) over the event-timed "
                         "decoder kernels of the running step; the tensor-core engine issues 3 fp16 MMA passes per logical GEMM "
                         "(split-fp16, fp32-level parity) on rows that need them",
-                "whole_step_tflops": in_step, "rows_fwd_per_step": rows_f / args.steps, "rows_grad_per_step": rows_g / args.steps}
+                "whole_step_tflops": in_step, "rows_fwd_per_step": rows_f / args.steps, "rows_grad_per_step": rows_g / args.steps,
+                "rows_grad_from_mask_cache_per_step": rows_gc / args.steps}
         # ---- CPU baseline (oracle port) on a bounded sample, rank 0 at N=1 only
         if world == 1 and not args.no_cpu_baseline:
             cpu_baseline = cpu_port_baseline(synth, lat_h, R_h, T_h)

@@ -50,11 +50,12 @@ class March(C.Structure):
 
 WS_FIELDS = ["ray", "entry", "exit_", "dist", "z", "flags", "nreal", "top_sdf", "top_pt", "top_zafter", "top_zgen",
              "list_a", "list_b", "pts", "sdf", "counts", "sdf_origin", "entry0", "top_lvl", "pyr_f", "pyr_i", "pyr_b",
-             "seg_approx", "sprev", "rq_idx", "rq_pts", "rq_sdf", "rq_cnt", "tile_counters", "view_stat"]
+             "seg_approx", "sprev", "rq_idx", "rq_pts", "rq_sdf", "rq_cnt", "mask_buf", "mask_base", "top_slot", "bm_row", "bm_slot",
+             "bm_sdf", "bm_coef", "bm_dpts", "bm_cnt", "tile_counters", "mask_cap", "view_stat"]
 
 
 class Workspace(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in WS_FIELDS]
+    _fields_ = [(n, C.c_int64 if n == "mask_cap" else C.c_void_p) for n in WS_FIELDS]
 
 
 # name -> (restype, argtypes); mirrors include/dist_b200.h one to one
@@ -70,6 +71,10 @@ PROTOTYPES = {
                                        C.c_void_p, C.c_void_p]),
     "dist_decoder_forward_tiers": (C.c_int, [C.POINTER(Net), C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_float,
                                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dist_decoder_forward_masks": (C.c_int, [C.POINTER(Net), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
+                                             C.c_void_p]),
+    "dist_decoder_backward_masked": (C.c_int, [C.POINTER(Net), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float,
+                                               C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dist_decoder_input_grad": (C.c_int, [C.POINTER(Net), C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_float,
                                           C.c_void_p, C.c_void_p, C.c_void_p]),
     "dist_decoder_backward": (C.c_int, [C.POINTER(Net), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,

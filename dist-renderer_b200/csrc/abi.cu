@@ -48,6 +48,9 @@ int mlp_launch(const dist_net_t* net, const NetDev& nd, int engine, int mode, co
   int rc;
   if (engine == DIST_ENGINE_TC) {
     rc = mlp_tc_launch(net, nd, mode, a, stream);
+  } else if (mode == 3) {
+    set_error("the mask-cache replay (mode 3) exists on the tensor-core engine only");
+    rc = DIST_E_UNSUPPORTED;
   } else {
     // the fp32 engine knows one row range: a second segment is a second launch on the shifted arrays
     MlpArgs a1 = a;
@@ -194,6 +197,30 @@ int dist_decoder_forward_tiers(const dist_net_t* net, const float* points, int64
   a.points = points; a.n_host = n_screen; a.n2_host = n_exact; a.seg2_offset = exact_offset; a.clamp_dist = 0.f; a.sdf = sdf;
   a.screen_seg1 = 1; a.screen_thresh = screen_thresh; a.seg_approx = seg_approx; a.tile_counters = tile_counters;
   return mlp_launch(net, nd, DIST_ENGINE_TC, 0, a, (cudaStream_t)stream);
+}
+
+int dist_decoder_forward_masks(const dist_net_t* net, const float* points, int64_t n, float* sdf, uint32_t* mask_buf,
+                               int64_t mask_cap, int64_t mask_base, void* stream) {
+  NetDev nd;
+  int rc = make_netdev(net, &nd);
+  if (rc) return rc;
+  DIST_REQUIRE(mask_buf && mask_cap > 0 && mask_base >= 0, "decoder_forward_masks: mask buffer required");
+  MlpArgs a{};
+  a.points = points; a.n_host = n; a.clamp_dist = 0.f; a.sdf = sdf;
+  a.mask_buf = mask_buf; a.mask_cap = mask_cap; a.mask_base_host = mask_base;
+  return mlp_launch(net, nd, DIST_ENGINE_TC, 0, a, (cudaStream_t)stream);
+}
+
+int dist_decoder_backward_masked(const dist_net_t* net, const int32_t* slots, const float* sdf_in, const float* coef, int64_t n,
+                                 float clamp_dist, const uint32_t* mask_buf, int64_t mask_cap, float* dpoints, float* acc0,
+                                 float* accl, void* stream) {
+  NetDev nd;
+  int rc = make_netdev(net, &nd);
+  if (rc) return rc;
+  MlpArgs a{};
+  a.n_host = n; a.clamp_dist = clamp_dist; a.grad = dpoints; a.coef = coef; a.acc0 = acc0; a.accl = accl;
+  a.mask_buf = const_cast<uint32_t*>(mask_buf); a.mask_cap = mask_cap; a.slots = slots; a.sdf_in = sdf_in;
+  return mlp_launch(net, nd, DIST_ENGINE_TC, 3, a, (cudaStream_t)stream);
 }
 
 int dist_decoder_input_grad(const dist_net_t* net, int engine, const float* points, int64_t n_host,

@@ -63,6 +63,15 @@ struct MlpArgs {
   float screen_thresh;      // one-pass values stand where every row of the 64-row half-tile has |sdf| > screen_thresh
   uint8_t* seg_approx;      // [rows / 64] out: 1 = this half-tile's sdf are one-pass values
   unsigned long long* tile_counters;  // optional [2]: tile programs evaluated with one / with three passes
+  // ReLU-mask cache of the tensor-core engine (mlp_tc.cu): a forward launch (mode 0) records the sign bits of every hidden
+  // layer for the rows it evaluates at full precision in its first sweep, at slots mask_base + row index (of segment 2
+  // when segment 1 is screened, of the only segment otherwise); mode 3 replays the transposed chain from them.
+  uint32_t* mask_buf;       // [16 * (n_layers - 1)][mask_cap] (one word per hidden layer and 32-feature block) or null
+  int64_t mask_cap;
+  int64_t mask_base_host;   // used when mask_base_dev is null
+  const int32_t* mask_base_dev;
+  const int32_t* slots;     // mode 3: [n] mask slot per row (-1: row contributes nothing)
+  const float* sdf_in;      // mode 3: [n] recorded decoder output per row
 };
 int mlp_simt_launch(const NetDev& net, int mode, const MlpArgs& a, cudaStream_t stream);
 int mlp_tc_launch(const dist_net_t* net, const NetDev& nd, int mode, const MlpArgs& a, cudaStream_t stream);

@@ -105,7 +105,7 @@ __device__ __forceinline__ void sphere_geom(const float (&c)[3], const float (&r
 // largest |sdf| if it beats it -- one pass over B values and one record write per sample instead of shifting a sorted list
 // (the march update kernel is bound by exactly this traffic).  k_finalize sorts each ray's records once, ascending.
 __device__ __forceinline__ void topk_insert(const dist_workspace_t& ws, int P, int B, int lp, float sdf, float px, float py,
-                                            float pz, float zafter, float zgen, int lvl) {
+                                            float pz, float zafter, float zgen, int lvl, int slot = -1) {
   const float asdf = fabsf(sdf);
   int pos = 0;
   float worst = -1.f;
@@ -118,6 +118,7 @@ __device__ __forceinline__ void topk_insert(const dist_workspace_t& ws, int P, i
   ws.top_zafter[(size_t)pos * P + lp] = zafter;
   ws.top_zgen[(size_t)pos * P + lp] = zgen;
   ws.top_lvl[(size_t)pos * P + lp] = (uint8_t)lvl;
+  if (ws.top_slot) ws.top_slot[(size_t)pos * P + lp] = slot;      // mask-cache slot of the sample's decoder row (-1: none)
   ws.top_pt[((size_t)pos * 3 + 0) * P + lp] = px;
   ws.top_pt[((size_t)pos * 3 + 1) * P + lp] = py;
   ws.top_pt[((size_t)pos * 3 + 2) * P + lp] = pz;
@@ -130,6 +131,7 @@ struct Level {
   uint8_t* hit;             // [P] max-pooled sphere-hit mask (renderer.py:668-680)
   int32_t* list;            // [P]
   int32_t* count;           // [1]
+  int32_t* s_slot;          // [3][P] mask-cache slot of each recorded sample's decoder row (-1: none)
 };
 
 // p = M^T (c + ray * depth)   (renderer.py:202-223, :119)
@@ -186,6 +188,7 @@ __global__ void k_setup(Cam cam, dist_march_t mp, dist_workspace_t ws, float* Zd
       ws.top_zafter[(size_t)b * P + lp] = 0.f;
       ws.top_zgen[(size_t)b * P + lp] = nanf("");
       ws.top_lvl[(size_t)b * P + lp] = 0;
+      if (ws.top_slot) ws.top_slot[(size_t)b * P + lp] = -1;
 #pragma unroll
       for (int k = 0; k < 3; ++k) ws.top_pt[((size_t)b * 3 + k) * P + lp] = 0.f;
     }
@@ -204,7 +207,8 @@ __global__ void k_setup(Cam cam, dist_march_t mp, dist_workspace_t ws, float* Zd
           for (int st = 0; st < ns; ++st)
             topk_insert(ws, P, mp.buffer_size, lp, L.s_sdf[(size_t)st * L.P + pp], L.s_pt[((size_t)st * 3 + 0) * L.P + pp],
                         L.s_pt[((size_t)st * 3 + 1) * L.P + pp], L.s_pt[((size_t)st * 3 + 2) * L.P + pp],
-                        L.s_zabs[(size_t)st * L.P + pp] - entry, L.s_zgen[(size_t)st * L.P + pp], lv);
+                        L.s_zabs[(size_t)st * L.P + pp] - entry, L.s_zgen[(size_t)st * L.P + pp], lv,
+                        L.s_slot[(size_t)st * L.P + pp]);
         }
       }
     }
@@ -310,10 +314,13 @@ __global__ void k_pyr_start(Cam cam, Level L, Level parent, int has_parent, cons
 
 // one trivial march step of a coarse level (renderer.py:472-510 via :773): every listed ray advances, samples are
 // recorded per (step, ray); the query point of the next step overwrites this thread's own slot
-__global__ void k_pyr_step(Cam cam, dist_march_t mp, Level L, int step, float* pts, const float* sdfbuf) {
+__global__ void k_pyr_step(Cam cam, dist_march_t mp, Level L, int step, float* pts, const float* sdfbuf, int64_t slot_base,
+                           int64_t slot_cap) {
   const int n = *L.count;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const int id = L.list[i];
+    // (the decoder launch of this step recorded row i at mask-cache slot slot_base + i; < 0: cache off)
+    L.s_slot[(size_t)step * L.P + id] = (slot_base >= 0 && slot_base + i < slot_cap) ? (int32_t)(slot_base + i) : -1;
     float c[3];
     load_view_pos(cam, id / L.Pv, c);
     const float sdf = sdfbuf[i];
@@ -332,9 +339,10 @@ __global__ void k_pyr_step(Cam cam, dist_march_t mp, Level L, int step, float* p
 }
 
 // the origin (filler samples, renderer.py:539-540) is the only row of segment 2 at step 0: always at full precision
-__global__ void k_append_origin(dist_workspace_t ws, int SEG) {
+__global__ void k_append_origin(dist_workspace_t ws, int SEG, int mask_slots_used) {
   ws.pts[(size_t)SEG * 3] = 0.f; ws.pts[(size_t)SEG * 3 + 1] = 0.f; ws.pts[(size_t)SEG * 3 + 2] = 0.f;
   ws.counts[1] = 1;
+  if (ws.mask_base) ws.mask_base[0] = mask_slots_used;    // the coarse pyramid levels recorded their rows before the march
 }
 
 // ---------------------------------------------------------------------------------------------- one march step
@@ -349,6 +357,11 @@ __global__ void k_march_update(Cam cam, dist_march_t mp, dist_workspace_t ws, in
   const float* pts_cur = ws.pts + (size_t)(step & 1) * (size_t)(2 * SEG) * 3;       // points of this step
   float* pts_nxt = ws.pts + (size_t)((step + 1) & 1) * (size_t)(2 * SEG) * 3;       // points of the next step
   if (step == 0 && blockIdx.x == 0 && threadIdx.x == 0) ws.sdf_origin[0] = ws.sdf[SEG];
+  // mask cache: the decoder launch of this step recorded the rows of segment 2 at slots mask_base[step] + (i - SEG)
+  const bool mc = scr && ws.mask_buf != nullptr;
+  const int mbase = mc ? ws.mask_base[step] : 0;
+  if (mc && blockIdx.x == 0 && threadIdx.x == 0)
+    ws.mask_base[step + 1] = mbase + (ws.counts[2 * step + 1] + 127) / 128 * 128;   // (slots are handed out tile by tile)
   const int B = mp.buffer_size;
   const float far_thresh = mp.clamp_dist + mp.screen_margin;
   for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
@@ -384,7 +397,9 @@ __global__ void k_march_update(Cam cam, dist_march_t mp, dist_workspace_t ws, in
       if (!(asdf <= 1.0f)) atomicOr(ws.view_stat + VS_STRIDE * v + VS_NONFINITE, 1);
       // marching depth relative to the true sphere entry (renderer.py:800-804 for the pyramid variant)
       const float zstore = (mp.marching_type == DIST_MARCH_PYRAMID) ? (znew + entry) - ws.entry0[lp] : znew;
-      topk_insert(ws, P, B, lp, sdf, px, py, pz, zstore, entry + zc, approx ? LVL_APPROX : 0);
+      int slot = -1;
+      if (mc && i >= SEG && (int64_t)mbase + (i - SEG) < ws.mask_cap) slot = mbase + (i - SEG);
+      topk_insert(ws, P, B, lp, sdf, px, py, pz, zstore, entry + zc, approx ? LVL_APPROX : 0, slot);
       if (step + 1 < mp.march_step) {
         if (mp.marching_type == DIST_MARCH_TRIVIAL) live = true;
         else live = (znew + entry < ws.exit_[lp]) && (asdf >= mp.threshold);  // renderer.py:559-561
@@ -431,11 +446,14 @@ __global__ void k_requery_gen(dist_march_t mp, dist_workspace_t ws, int P) {
   }
 }
 
-__global__ void k_requery_apply(dist_workspace_t ws, int P) {
+__global__ void k_requery_apply(dist_workspace_t ws, int P, int base_index) {
   const int n = *ws.rq_cnt;
+  const bool mc = ws.mask_buf != nullptr && ws.top_slot != nullptr;
+  const int mbase = mc ? ws.mask_base[base_index] : 0;      // the re-query launch recorded its rows at mbase + i
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const int lp = ws.rq_idx[i] / DIST_MAX_BUFFER, b = ws.rq_idx[i] % DIST_MAX_BUFFER;
     ws.top_sdf[(size_t)b * P + lp] = ws.rq_sdf[i];
+    if (mc) ws.top_slot[(size_t)b * P + lp] = ((int64_t)mbase + i < ws.mask_cap) ? mbase + i : -1;
     ws.top_lvl[(size_t)b * P + lp] = (uint8_t)((ws.top_lvl[(size_t)b * P + lp] & ~LVL_APPROX) | LVL_REQUERIED);
   }
 }
@@ -465,7 +483,8 @@ __global__ void k_finalize(dist_march_t mp, dist_workspace_t ws, float* Zdepth, 
       const float r_p[3] = {ws.top_pt[((size_t)j * 3 + 0) * P + lp], ws.top_pt[((size_t)j * 3 + 1) * P + lp],
                             ws.top_pt[((size_t)j * 3 + 2) * P + lp]};
       const int r_lvl = ws.top_lvl[(size_t)j * P + lp];
-      for (int i = 0; i < B - S; ++i) topk_insert(ws, P, B, lp, r_sdf, r_p[0], r_p[1], r_p[2], r_za, r_zg, r_lvl);
+      const int r_slot = ws.top_slot ? ws.top_slot[(size_t)j * P + lp] : -1;
+      for (int i = 0; i < B - S; ++i) topk_insert(ws, P, B, lp, r_sdf, r_p[0], r_p[1], r_p[2], r_za, r_zg, r_lvl, r_slot);
     }
     nreal = B;
     ws.nreal[lp] = B;
@@ -478,6 +497,7 @@ __global__ void k_finalize(dist_march_t mp, dist_workspace_t ws, float* Zdepth, 
         t = ws.top_zafter[x]; ws.top_zafter[x] = ws.top_zafter[y]; ws.top_zafter[y] = t;
         t = ws.top_zgen[x]; ws.top_zgen[x] = ws.top_zgen[y]; ws.top_zgen[y] = t;
         const uint8_t l = ws.top_lvl[x]; ws.top_lvl[x] = ws.top_lvl[y]; ws.top_lvl[y] = l;
+        if (ws.top_slot) { const int32_t sl = ws.top_slot[x]; ws.top_slot[x] = ws.top_slot[y]; ws.top_slot[y] = sl; }
         for (int k = 0; k < 3; ++k) {
           const size_t px = ((size_t)b * 3 + k) * P + lp, py = ((size_t)(b - 1) * 3 + k) * P + lp;
           t = ws.top_pt[px]; ws.top_pt[px] = ws.top_pt[py]; ws.top_pt[py] = t;
@@ -543,8 +563,11 @@ __global__ void k_normal_finish(Cam cam, const int32_t* idx_in, const float* gra
 }
 
 // ---------------------------------------------------------------------------------------------- backward rows
+// Replay rows of the backward: one per selected sample with a non-zero upstream coefficient.  Samples whose decoder row left
+// its ReLU masks in the mask cache (ws.top_slot >= 0) go to the "masked" list (ws.bm_*: transposed chain only), the others
+// (fillers, coarse pyramid samples, rows of re-evaluated tiles, everything when the cache is off) to the full replay list.
 __global__ void k_bwd_gen(dist_march_t mp, dist_workspace_t ws, const float* gZ, const float* gM, int32_t* row_pix,
-                          float* pts, float* coef, int32_t* count, int P) {
+                          float* pts, float* coef, int32_t* count, int P, int use_masks) {
   const int lp = blockIdx.x * blockDim.x + threadIdx.x;
   const bool hit = lp < P && (ws.flags[lp] & 1);
   const int B = mp.buffer_size;
@@ -552,20 +575,26 @@ __global__ void k_bwd_gen(dist_march_t mp, dist_workspace_t ws, const float* gZ,
   const float gz = (hit && gZ) ? gZ[lp] : 0.f;
   const float gm = (hit && gM) ? gM[lp] : 0.f;
   for (int b = 0; b < B; ++b) {
-    float cf = 0.f;
+    float cf = 0.f, s = 0.f;
+    int slot = -1;
     if (hit) {
       const float sb = ws.top_sdf[(size_t)b * P + lp];
-      const float s = (sb != 1.0f) ? sb : so;
+      s = (sb != 1.0f) ? sb : so;
       const bool cm = (s >= -mp.clamp_dist) && (s <= mp.clamp_dist);
       cf = cm ? mp.ratio * gz : 0.f;  // renderer.py:414-417
       if (b == 0) cf += gm;           // renderer.py:386 (unclamped re-query at the min-|sdf| sample)
+      if (use_masks && sb != 1.0f) slot = ws.top_slot[(size_t)b * P + lp];
     }
-    const int idx = warp_append(count, cf != 0.f);
+    const int idx = warp_append(count, cf != 0.f && slot < 0);
     if (idx >= 0) {
       row_pix[idx] = lp * DIST_MAX_BUFFER + b;
       coef[idx] = cf;
 #pragma unroll
       for (int k = 0; k < 3; ++k) pts[(size_t)idx * 3 + k] = ws.top_pt[((size_t)b * 3 + k) * P + lp];
+    }
+    if (use_masks) {
+      const int im = warp_append(ws.bm_cnt, cf != 0.f && slot >= 0);
+      if (im >= 0) { ws.bm_row[im] = lp * DIST_MAX_BUFFER + b; ws.bm_slot[im] = slot; ws.bm_sdf[im] = s; ws.bm_coef[im] = cf; }
     }
   }
 }
@@ -649,7 +678,9 @@ static void carve_levels(const Cam& cam, const dist_workspace_t* ws, Level* L1, 
   uint8_t* bb = ws->pyr_b;
   const int w1 = (w + 1) / 2, h1 = (h + 1) / 2, w2 = (w1 + 1) / 2, h2 = (h1 + 1) / 2;
   const int dims[2][2] = {{w1, h1}, {w2, h2}};
-  int32_t* counts = li + ((size_t)w1 * h1 + (size_t)w2 * h2) * cam.n_views;
+  // pyr_i: [lists P1 + P2][slots 3 (P1 + P2)][8 counters]
+  int32_t* slots = li + ((size_t)w1 * h1 + (size_t)w2 * h2) * cam.n_views;
+  int32_t* counts = li + 4 * ((size_t)w1 * h1 + (size_t)w2 * h2) * cam.n_views;
   for (int i = 0; i < 2; ++i) {
     Level& L = *Ls[i];
     L.w = dims[i][0]; L.h = dims[i][1]; L.Pv = L.w * L.h; L.P = L.Pv * cam.n_views; L.scale = (i == 0) ? 2 : 4;
@@ -662,6 +693,7 @@ static void carve_levels(const Cam& cam, const dist_workspace_t* ws, Level* L1, 
     L.s_zgen = f; f += 3 * (size_t)L.P;
     L.hit = bb; bb += L.P;
     L.list = li; li += L.P;
+    L.s_slot = slots; slots += 3 * (size_t)L.P;
     L.count = counts + i;
   }
 }
@@ -699,9 +731,18 @@ int render_depth_fwd(const dist_net_t* net, int engine, const dist_camera_t* cam
   } else {
     wsv.seg_approx = nullptr;     // the kernels key on seg_approx
   }
+  // mask cache (tensor-core engine with two precision tiers only)
+  const bool mc = scr && ws->mask_buf != nullptr;
+  if (mc) {
+    DIST_REQUIRE(ws->mask_base && ws->top_slot && ws->mask_cap > 0 && ws->mask_cap < (int64_t)1 << 31, "workspace: mask cache buffers missing");
+    DIST_CHECK_CUDA(cudaMemsetAsync(ws->mask_base, 0, sizeof(int32_t) * (S_total + 3), st));
+  } else {
+    wsv.mask_buf = nullptr; wsv.top_slot = nullptr;
+  }
   ws = &wsv;
   Level L1, L2;
   memset(&L1, 0, sizeof(L1)); memset(&L2, 0, sizeof(L2));
+  int64_t coarse_slots = 0;      // mask-cache slots taken by the coarse pyramid levels
   if (pyr) {
     DIST_REQUIRE(ws->pyr_f && ws->pyr_i && ws->pyr_b, "workspace: pyramid buffers missing");
     const bool full_image = cam.row0 == 0 && cam.row_step == cam.row_group && cam.n_rows == cam.H;
@@ -729,9 +770,13 @@ int render_depth_fwd(const dist_net_t* net, int engine, const dist_camera_t* cam
         MlpArgs a{};
         a.points = ws->pts; a.n_host = L.P; a.n_dev = L.count; a.clamp_dist = 0.f; a.sdf = ws->sdf; a.rows_evaluated = rows_eval;
         a.tile_counters = ws->tile_counters;
+        // mask cache: a coarse step's rows take L.P slots (its capacity), handed out in launch order
+        const int64_t slot_base = mc ? coarse_slots : -1;
+        if (mc) { a.mask_buf = ws->mask_buf; a.mask_cap = ws->mask_cap; a.mask_base_host = slot_base; coarse_slots += (L.P + 127) / 128 * 128; }
         rc = mlp_launch(net, nd, engine, 0, a, st);
         if (rc) return rc;
-        k_pyr_step<<<min((L.P + tb - 1) / tb, 4 * num_sms()), tb, 0, st>>>(cam, *mp, L, s, ws->pts, ws->sdf); count_launch();
+        k_pyr_step<<<min((L.P + tb - 1) / tb, 4 * num_sms()), tb, 0, st>>>(cam, *mp, L, s, ws->pts, ws->sdf, slot_base,
+                                                                           mc ? ws->mask_cap : 0); count_launch();
       }
     }
   }
@@ -739,7 +784,7 @@ int render_depth_fwd(const dist_net_t* net, int engine, const dist_camera_t* cam
   DIST_CHECK_CUDA(cudaMemsetAsync(ws->counts, 0, sizeof(int32_t) * 2 * (S_total + 2), st));
   k_setup<<<(cam.n_views * setup_threads_per_view(cam.W, cam.n_rows) + tb - 1) / tb, tb, 0, st>>>(cam, *mp, *ws, Zdepth, mask, min_sdf, P,
                                                                                                 L1, L2); count_launch();
-  k_append_origin<<<1, 1, 0, st>>>(*ws, SEG); count_launch();
+  k_append_origin<<<1, 1, 0, st>>>(*ws, SEG, (int)coarse_slots); count_launch();
   DIST_CHECK_CUDA(cudaGetLastError());
   const int gu = min(gb, 4 * num_sms());
   for (int s = 0; s < S; ++s) {
@@ -751,6 +796,7 @@ int render_depth_fwd(const dist_net_t* net, int engine, const dist_camera_t* cam
     a.clamp_dist = 0.f; a.sdf = ws->sdf; a.rows_evaluated = rows_eval;
     a.tile_counters = ws->tile_counters;
     if (scr) { a.screen_seg1 = 1; a.screen_thresh = mp->clamp_dist + mp->screen_margin; a.seg_approx = ws->seg_approx; }
+    if (mc) { a.mask_buf = ws->mask_buf; a.mask_cap = ws->mask_cap; a.mask_base_dev = ws->mask_base + s; }
     rc = mlp_launch(net, nd, engine, 0, a, st);
     if (rc) return rc;
     k_march_update<<<gu, tb, 0, st>>>(cam, *mp, *ws, s, P); count_launch();
@@ -760,9 +806,10 @@ int render_depth_fwd(const dist_net_t* net, int engine, const dist_camera_t* cam
     MlpArgs a{};
     a.points = ws->rq_pts; a.n_host = (int64_t)P * mp->buffer_size; a.n_dev = ws->rq_cnt; a.clamp_dist = 0.f; a.sdf = ws->rq_sdf;
     a.tile_counters = ws->tile_counters;
+    if (mc) { a.mask_buf = ws->mask_buf; a.mask_cap = ws->mask_cap; a.mask_base_dev = ws->mask_base + S; }   // after the last step's rows
     rc = mlp_launch(net, nd, engine, 0, a, st);
     if (rc) return rc;
-    k_requery_apply<<<gu, tb, 0, st>>>(*ws, P); count_launch();
+    k_requery_apply<<<gu, tb, 0, st>>>(*ws, P, S); count_launch();
   }
   k_finalize<<<gb, tb, 0, st>>>(*mp, *ws, Zdepth, mask, min_sdf, P, cam.Pv); count_launch();
   DIST_CHECK_CUDA(cudaGetLastError());
@@ -807,17 +854,36 @@ int render_depth_bwd(const dist_net_t* net, int engine, const dist_camera_t* cam
   const int P = cam.Pv * cam.n_views;
   DIST_CHECK_CUDA(cudaMemsetAsync(s_count, 0, sizeof(int32_t), st));
   const int tb = 256, gb = (P + tb - 1) / tb;
-  k_bwd_gen<<<gb, tb, 0, st>>>(*mp, *ws, gZ, gM, s_row_pix, s_pts, s_coef, s_count, P); count_launch();
+  // samples whose decoder row left its ReLU masks in the cache are replayed with the transposed chain alone
+  const bool mc = engine == DIST_ENGINE_TC && ws->mask_buf && ws->top_slot && ws->bm_row && ws->bm_slot && ws->bm_sdf && ws->bm_coef &&
+                  ws->bm_dpts && ws->bm_cnt;
+  if (mc) DIST_CHECK_CUDA(cudaMemsetAsync(ws->bm_cnt, 0, sizeof(int32_t), st));
+  k_bwd_gen<<<gb, tb, 0, st>>>(*mp, *ws, gZ, gM, s_row_pix, s_pts, s_coef, s_count, P, mc ? 1 : 0); count_launch();
   MlpArgs a{};
   a.points = s_pts; a.n_host = (int64_t)P * mp->buffer_size; a.n_dev = s_count; a.clamp_dist = 0.f;
   a.grad = s_dpts; a.coef = s_coef; a.acc0 = acc0; a.accl = accl; a.rows_evaluated = rows_eval;
   rc = mlp_launch(net, nd, engine, 2, a, st);
   if (rc) return rc;
+  if (mc) {
+    MlpArgs b{};
+    b.n_host = (int64_t)P * mp->buffer_size; b.n_dev = ws->bm_cnt; b.clamp_dist = 0.f;
+    b.grad = ws->bm_dpts; b.coef = ws->bm_coef; b.acc0 = acc0; b.accl = accl;
+    b.rows_evaluated = rows_eval ? rows_eval + 1 : nullptr;      // counted apart: these rows cost F, not 2F
+    b.mask_buf = ws->mask_buf; b.mask_cap = ws->mask_cap; b.slots = ws->bm_slot; b.sdf_in = ws->bm_sdf;
+    rc = mlp_launch(net, nd, engine, 3, b, st);
+    if (rc) return rc;
+  }
   if (d_cam && d_ray) {
     const int w1 = (cam.W + 1) / 2, h1 = (cam.n_rows + 1) / 2, w2 = (w1 + 1) / 2, h2 = (h1 + 1) / 2;
-    k_bwd_scatter<<<min((int)(((int64_t)P * mp->buffer_size + tb - 1) / tb), 4 * num_sms()), tb, 0, st>>>(
-        cam, *ws, s_row_pix, s_dpts, s_count, d_cam, d_ray, d_ray_coarse, w1, w1 * h1, w2, w2 * h2, P,
-        mp->cam_grad_levels ? mp->cam_grad_levels : 3); count_launch();
+    const int gs = min((int)(((int64_t)P * mp->buffer_size + tb - 1) / tb), 4 * num_sms());
+    const int lv = mp->cam_grad_levels ? mp->cam_grad_levels : 3;
+    k_bwd_scatter<<<gs, tb, 0, st>>>(cam, *ws, s_row_pix, s_dpts, s_count, d_cam, d_ray, d_ray_coarse, w1, w1 * h1, w2, w2 * h2, P, lv);
+    count_launch();
+    if (mc) {
+      k_bwd_scatter<<<gs, tb, 0, st>>>(cam, *ws, ws->bm_row, ws->bm_dpts, ws->bm_cnt, d_cam, d_ray, d_ray_coarse, w1, w1 * h1, w2,
+                                       w2 * h2, P, lv);
+      count_launch();
+    }
   }
   DIST_CHECK_CUDA(cudaGetLastError());
   return DIST_OK;

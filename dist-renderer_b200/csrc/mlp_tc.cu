@@ -107,6 +107,13 @@ struct TcIO {
   float screen_thresh;          // a screened half-tile passes when all its rows have |sdf| > screen_thresh
   uint8_t* seg_approx;          // [rows / 64] out: 1 = the sdf of this 64-row half-tile are one-pass values
   unsigned long long* tile_counters;   // optional [2]: += tiles evaluated with one pass / with three passes
+  // ReLU-mask cache (see "mask cache" in the kernel comment).  MODE 0 writes, MODE 3 reads.
+  uint32_t* mask_buf;           // [mask words][mask_cap] one 32-bit word per (net layer, 32-feature block) and row slot
+  int64_t mask_cap;             // row slots in mask_buf
+  int64_t mask_base_host;       // first slot of this launch's full-precision rows (when mask_base_dev == nullptr); < 0: off
+  const int32_t* mask_base_dev;
+  const int32_t* slots;         // MODE 3: [n] mask slot of each row
+  const float* sdf_in;          // MODE 3: [n] the (unclamped) decoder output of each row, as recorded by the forward
 };
 
 // --------------------------------------------------------------------------------------------- PTX helpers
@@ -214,6 +221,8 @@ __device__ __forceinline__ void store_group_hi(uint8_t* smem, int region, int fe
 // --------------------------------------------------------------------------------------------- kernel
 // MODE 0: forward (sdf).  MODE 1: forward + transposed chain -> d clamp(sdf)/d xyz.  MODE 2: backward replay with per-row
 // upstream coefficients: d/dxyz per row and the row-summed pre-activation gradients of layer 0 / the latent_in layer.
+// MODE 3: MODE 2 without its forward half: the ReLU sign bits come from the mask cache a MODE 0 launch wrote (io.slots), the
+// decoder output from io.sdf_in; only the transposed chain runs (program layers n_mma .. 2 n_mma - 1).
 template <int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
 mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_hi, const TcParams P, const TcIO io) {
@@ -231,6 +240,11 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
   auto lim_of = [&](int64_t t) -> int64_t { return (t < tiles1) ? n1 : io.seg2_offset + n2; };
   if (blockIdx.x == 0 && tid == 0 && io.rows_evaluated)
     atomicAdd(reinterpret_cast<unsigned long long*>(io.rows_evaluated), (unsigned long long)n);
+  // ---- mask cache: a MODE 0 launch records, for every row it evaluates at full precision in its first sweep, the ReLU sign
+  // bits of all hidden layers (one word per layer and 32-feature block, 512 B per row for the 8x512 network) at slot
+  // mask_base + (index of the row among those rows).  The backward replay (MODE 3) then runs the transposed chain alone:
+  // the forward half of MODE 2 only existed to recompute these bits.
+  const int64_t mask_base = (MODE == 0 && io.mask_buf) ? (io.mask_base_dev ? (int64_t)*io.mask_base_dev : io.mask_base_host) : -1;
 
   long long dbg_c0 = 0, dbg_t0 = 0;
   if (io.dbg_out && blockIdx.x == 0 && tid == 0) { dbg_c0 = clock64(); asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0)); }
@@ -244,6 +258,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
   const uint32_t FIN = bar0 + 8 * (2 * NST + 36);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 8 * (2 * NST + 37));
   const int n_prog = P.n_prog;
+  const int m0 = (MODE == 3) ? P.n_mma : 0;      // first program layer of a tile
 
   // ---- two-tier precision (MODE 0 with io.screen_seg1): a tile of the first row segment is first evaluated with ONE fp16 pass
   // (A_hi W_hi; only the hi halves of the weight stages are fetched).  If all 64 rows of a CTA come out with
@@ -308,7 +323,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
       for (int phase = 0; phase < 2; ++phase) {
         for (int i = next_tile(phase, -1); i >= 0; i = next_tile(phase, i)) {
           const bool exact = !(phase == 0 && i < c1);      // one-pass tiles come in pairs that share one weight stream
-          for (int m = 0; m < n_prog; ++m) {
+          for (int m = m0; m < n_prog; ++m) {
             const int kc32 = P.L[m].kc32, sb = P.L[m].stage_base;
             // full precision: one ring slot = one 32-wide K chunk, [hi 8 KB][lo 8 KB] per CTA.
             // one pass: one ring slot = the hi halves of TWO consecutive K chunks (the same bytes in flight per slot: the ring
@@ -366,13 +381,13 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
         const bool exact = !(phase == 0 && i < c1);   // pair mode: two one-pass tiles, A_hi W_hi only
         const bool has_b = !exact && (i + 1 < c1);    // (an odd count leaves the last pair with one tile)
         (void)t;
-        for (int m = 0; m < n_prog; ++m, ++G) {
+        for (int m = m0; m < n_prog; ++m, ++G) {
           const int kc32 = P.L[m].kc32, nh = P.L[m].nh;
           const uint32_t buf = exact ? (G & 1) : 0u;
           // The last accumulator of the previous tile lives in a TMEM buffer until its epilogue drained it (FIN).  Single tiles
           // ping-pong between the two buffers layer by layer, so layer 0 may start early and only layer 1 waits; a pair uses
           // both buffers in every layer, so a pair -- and the tile after a pair -- waits before its layer 0.
-          if (!d_first && m == ((!exact || prev_pair) ? 0 : 1)) { mbar_wait_cluster(FIN, fin_phase); fin_phase ^= 1; }
+          if (!d_first && m == m0 + ((!exact || prev_pair) ? 0 : 1)) { mbar_wait_cluster(FIN, fin_phase); fin_phase ^= 1; }
           // N-half outer, K block inner: half 0 of the accumulator completes while half 1 is still being computed, so
           // its epilogue (the first A blocks of the next layer) overlaps the second pass.  A_FREE(kc) tells the epilogue
           // when the last pass has consumed A block kc and its slot may be overwritten in place.
@@ -516,6 +531,19 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
     uint32_t mk[DIST_MAX_LAYERS][2];     // ReLU sign bits of this thread's (row, 32 features x 2 halves) per net layer
     float acc0r[2] = {0.f, 0.f}, acclr[2] = {0.f, 0.f};  // MODE 2: per-lane running column sums
 
+    // mask-cache slot of this thread's row in tile t (-1: not recorded): only rows evaluated at full precision in the first
+    // sweep -- the second row segment when the first is screened, every row of a plain single-segment launch
+    auto rec_slot = [&](int64_t t) -> int64_t {
+      if (MODE != 0 || mask_base < 0) return -1;
+      const int64_t r = row0_of(t) + rank * 64 + row;
+      if (r >= lim_of(t)) return -1;
+      int64_t idx;
+      if (io.screen_seg1) { if (t < tiles1) return -1; idx = r - io.seg2_offset; }
+      else { if (n2 > 0) return -1; idx = r; }
+      const int64_t sl = mask_base + idx;
+      return (sl < io.mask_cap) ? sl : -1;
+    };
+    const bool rec_on = (MODE == 0) && mask_base >= 0;
     auto load_point = [&](int64_t t) {
       const int64_t gr = row0_of(t) + rank * 64 + row;
       if (gr < lim_of(t)) { px = io.points[gr * 3]; py = io.points[gr * 3 + 1]; pz = io.points[gr * 3 + 2]; }
@@ -527,7 +555,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
       if (lane == 0) mbar_arrive_cluster(A_FULL(kc), 0);
     };
     // layer 0 on CUDA cores: A <- split(sA * relu(b0' + W0 xyz)) for this thread's 32-feature blocks
-    auto layer0 = [&]() {
+    auto layer0 = [&](int64_t slot) {
       const int kblocks = P.L[0].kc32;                          // 32-feature blocks the first MMA layer consumes
       const int nh0 = (P.N0 + 255) >> 8;
       for (int h = 0; h < nh0; ++h) {
@@ -553,6 +581,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
           store_group(smem, f0 + 8 * g, row, x);
         }
         if (MODE != 0) mk[0][h] = m0;
+        if (MODE == 0 && slot >= 0) io.mask_buf[(size_t)kb * io.mask_cap + slot] = m0;      // mask cache: net layer 0
         signal_block(kb);
       }
     };
@@ -616,14 +645,53 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
         signal_block(kb);
       }
     };
+    // MODE 3: start of a tile = its row scalars, its ReLU masks from the cache, and the seed of the transposed chain
+    // (delta of the last hidden layer: w_last[f] * relu'(f), unit upstream) as the A operand of the first program layer
+    float seed_scale = 0.f;
+    auto seed = [&](int64_t t) {
+      const int64_t r = row0_of(t) + rank * 64 + row;
+      const bool ok = r < lim_of(t);
+      int64_t sl = -1;
+      float o = 0.f, cf = 0.f;
+      if (ok) { sl = io.slots[r]; o = io.sdf_in[r]; cf = io.coef ? io.coef[r] : 1.f; }
+      float d = 1.f - o * o;                                  // tanh' at the recorded output (deep_sdf_decoder.py:109-110)
+      if (P.use_tanh) { const float t1 = atanhf(o); d *= (1.f - t1 * t1); }
+      bool uc = io.clamp_dist > 0.f;
+      if (io.use_clamp) uc = ok ? (io.use_clamp[r] != 0) : false;
+      if (uc && !(o >= -io.clamp_dist && o <= io.clamp_dist)) d = 0.f;
+      seed_scale = (ok && sl >= 0) ? d * cf : 0.f;
+      for (int l = 0; l <= n_mma; ++l)
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+          mk[l][h] = (ok && sl >= 0) ? io.mask_buf[((size_t)l * 16 + (8 * h + 4 * q + ch)) * io.mask_cap + sl] : 0u;
+      const int LNl = P.L[n_mma - 1].N, kblocks = P.L[n_mma].kc32;
+      for (int h = 0; h < 2; ++h) {
+        const int kb = 8 * h + 4 * q + ch;
+        if (kb >= kblocks) continue;
+        const int f0 = 32 * kb;
+        const uint32_t mb = mk[n_mma][h];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float x[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int f = f0 + 8 * g + e;
+            x[e] = (f < LNl && ((mb >> (8 * g + e)) & 1u)) ? __ldg(P.wlast + f) * sD : 0.f;
+          }
+          store_group(smem, f0 + 8 * g, row, x);
+        }
+        signal_block(kb);
+      }
+    };
     // what the next tile needs before the current one is drained: its points, then (A being free) its layer 0
     auto prefetch_points = [&](int phase, int inext) {
-      if (inext < 0) return;
+      if (inext < 0 || MODE == 3) return;
       if (phase == 0 && inext < c1) load_points_pair(inext); else load_point(tile_of(inext));
     };
     auto start_layer0 = [&](int phase, int inext) {
       if (inext < 0) return;
-      if (phase == 0 && inext < c1) layer0_pair(); else layer0();
+      if (MODE == 3) { seed(tile_of(inext)); return; }
+      if (phase == 0 && inext < c1) layer0_pair(); else layer0(rec_slot(tile_of(inext)));
     };
     // the whole forward program of one pair (tiles i and, if has_b, i + 1 of this cluster's list)
     auto run_pair = [&](int i, int inext, bool has_b) {
@@ -743,9 +811,10 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
       }
       const int64_t gr = row0_of(t) + rank * 64 + row;
       const bool row_ok = gr < lim_of(t);
-      float dot = 0.f, rowscale = 0.f, dx = 0.f, dy = 0.f, dz = 0.f;
+      const int64_t slot = rec_slot(t);
+      float dot = 0.f, rowscale = (MODE == 3) ? seed_scale : 0.f, dx = 0.f, dy = 0.f, dz = 0.f;
       uint32_t mk0s[2] = {0u, 0u};
-      for (int m = 0; m < n_prog; ++m, ++G) {
+      for (int m = m0; m < n_prog; ++m, ++G) {
         const uint32_t buf = G & 1;
         const bool fwd = m < n_mma;
         const bool fwd_last = (m == n_mma - 1);
@@ -807,7 +876,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
                 for (int e = 0; e < 4; ++e) {
                   const int j = 4 * j4 + e;
                   const float a = fmaf(v[j], cscale, bb[e]);
-                  if (MODE != 0) mb |= (a > 0.f) ? (1u << j) : 0u;
+                  if (MODE != 0 || rec_on) mb |= (a > 0.f) ? (1u << j) : 0u;
                   v[j] = fmaxf(a, 0.f);
                 }
               }
@@ -826,6 +895,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
               }
             }
             if (MODE != 0) mk[m + 1][h] = mb;
+            if (MODE == 0 && slot >= 0) io.mask_buf[((size_t)(m + 1) * 16 + kb) * io.mask_cap + slot] = mb;   // mask cache
             if (fwd_last) {
               if (interior) {
 #pragma unroll
@@ -892,7 +962,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
               for (int g = 0; g < 4; ++g) store_group(smem, fb + 8 * g, row, &v[8 * g]);
               signal_block(kb);
             }
-            if (MODE == 2 && (prog_last || m == P.acc_l_prog)) {
+            if ((MODE == 2 || MODE == 3) && (prog_last || m == P.acc_l_prog)) {
               // row-sum of rowscale * delta for the latent gradient; column j of this 32-block ends in lane j
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] *= rowscale;
@@ -984,11 +1054,11 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
       }
     }
     if (io.tile_counters && rank == 0 && ew == 0 && lane == 0) {
-      if (MODE != 0) n_tiles_3pass = 2u * (unsigned)cnt;      // forward + transposed chain
+      if (MODE != 0) n_tiles_3pass = (MODE == 3 ? 1u : 2u) * (unsigned)cnt;      // forward + transposed chain
       if (n_tiles_1pass) atomicAdd(io.tile_counters, (unsigned long long)n_tiles_1pass);
       if (n_tiles_3pass) atomicAdd(io.tile_counters + 1, (unsigned long long)n_tiles_3pass);
     }
-    if (MODE == 2) {
+    if (MODE == 2 || MODE == 3) {
       // flush the per-lane running column sums: lane j of this warp holds column 32*kb + j of its blocks
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
@@ -1027,7 +1097,8 @@ EncodeFn get_encode() {
 }  // namespace
 
 int mlp_tc_launch(const dist_net_t* net, const NetDev& nd, int mode, const MlpArgs& a, cudaStream_t stream) {
-  DIST_REQUIRE(mode >= 0 && mode <= 2, "tensor-core engine: bad mode %d", mode);
+  DIST_REQUIRE(mode >= 0 && mode <= 3, "tensor-core engine: bad mode %d", mode);
+  DIST_REQUIRE(mode != 3 || (a.slots && a.sdf_in && a.mask_buf && a.mask_cap > 0), "tensor-core engine: mode 3 needs the mask cache");
   DIST_REQUIRE(net->tc_blob && net->tc_scale, "tensor-core engine: operands not prepared (tc.prepare)");
   const int nl = nd.n_layers;
   DIST_REQUIRE(nl >= 4 && nl <= 10, "tensor-core engine: %d layers unsupported", nl);
@@ -1084,6 +1155,8 @@ int mlp_tc_launch(const dist_net_t* net, const NetDev& nd, int mode, const MlpAr
   io.screen_seg1 = (mode == 0) ? a.screen_seg1 : 0;
   io.screen_thresh = a.screen_thresh; io.seg_approx = a.seg_approx;
   io.tile_counters = a.tile_counters;
+  io.mask_buf = a.mask_buf; io.mask_cap = a.mask_cap; io.mask_base_host = a.mask_buf ? a.mask_base_host : -1;
+  io.mask_base_dev = a.mask_base_dev; io.slots = a.slots; io.sdf_in = a.sdf_in;
   DIST_REQUIRE(!io.screen_seg1 || io.seg_approx != nullptr, "tensor-core engine: two-tier precision needs seg_approx");
   DIST_REQUIRE((a.n2_host == 0 && !a.n2_dev) || (a.seg2_offset % 128 == 0 && a.seg2_offset >= a.n_host),
                "tensor-core engine: the second row segment must start at a multiple of 128 behind the first");
@@ -1118,6 +1191,7 @@ int mlp_tc_launch(const dist_net_t* net, const NetDev& nd, int mode, const MlpAr
     DIST_CHECK_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     DIST_CHECK_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     DIST_CHECK_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    DIST_CHECK_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr_done = true;
   }
   const int64_t tiles = (a.n_host + 127) / 128 + (a.n2_host + 127) / 128;   // capacities when the counts live on the device
@@ -1126,7 +1200,8 @@ int mlp_tc_launch(const dist_net_t* net, const NetDev& nd, int mode, const MlpAr
   if (clusters < 1) clusters = 1;
   if (mode == 0) { mlp_tc_kernel<0><<<clusters * 2, NTHREADS, SMEM_BYTES, stream>>>(tmap, tmap_hi, P, io); }
   else if (mode == 1) { mlp_tc_kernel<1><<<clusters * 2, NTHREADS, SMEM_BYTES, stream>>>(tmap, tmap_hi, P, io); }
-  else { mlp_tc_kernel<2><<<clusters * 2, NTHREADS, SMEM_BYTES, stream>>>(tmap, tmap_hi, P, io); }
+  else if (mode == 2) { mlp_tc_kernel<2><<<clusters * 2, NTHREADS, SMEM_BYTES, stream>>>(tmap, tmap_hi, P, io); }
+  else { mlp_tc_kernel<3><<<clusters * 2, NTHREADS, SMEM_BYTES, stream>>>(tmap, tmap_hi, P, io); }
   count_launch();
   DIST_CHECK_CUDA(cudaGetLastError());
   if (P.dbg & 4) {

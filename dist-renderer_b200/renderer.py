@@ -77,10 +77,21 @@ class _RenderDepthFn(torch.autograd.Function):
             "top_lvl": torch.empty(B, P, device=dev, dtype=torch.uint8),
         }
         scr = ren._scratch(pyramid=pyr)
+        # ReLU-mask cache (dist_workspace_t.mask_buf): when a backward will follow, the forward keeps the sign bits of the rows
+        # it evaluates at full precision (512 B per row for the 8x512 network), so that the backward replays the transposed
+        # chain alone.  Sized for `mask_rows_per_ray` such rows per ray; rows beyond that fall back to the full replay.
+        mask_cap = 0
+        if screen and ren.mask_cache and (opts["want_depth_grad"] or opts["want_mask_grad"]):
+            mask_cap = (int(ren.mask_rows_per_ray * P) + 127) // 128 * 128
+            saved["mask_buf"] = torch.empty(16 * (plan.n_layers - 1) * mask_cap, device=dev, dtype=torch.int32)
+            saved["top_slot"] = torch.empty(B, P, device=dev, dtype=torch.int32)
         ws = _abi.Workspace()
         for name in _abi.WS_FIELDS:
+            if name == "mask_cap":
+                continue
             t = saved.get(name, scr.get(name))
             setattr(ws, name, t.data_ptr() if t is not None else None)
+        ws.mask_cap = mask_cap
         ws.tile_counters = ren.tile_counters.data_ptr()
         Zdepth = torch.empty(P, **f32)
         mask = torch.empty(P, device=dev, dtype=torch.uint8)
@@ -88,7 +99,7 @@ class _RenderDepthFn(torch.autograd.Function):
         _abi.check(lib.dist_render_depth_fwd(net, engine, cam, mp, ws, _abi.ptr(Zdepth), _abi.ptr(mask),
                                              _abi.ptr(min_sdf), _abi.ptr(ren.rows_evaluated), st))
         ren._last_counts = scr["view_stat"]
-        ctx.ren, ctx.opts, ctx.engine, ctx.mp = ren, opts, engine, mp
+        ctx.ren, ctx.opts, ctx.engine, ctx.mp, ctx.mask_cap = ren, opts, engine, mp, mask_cap
         ctx.saved = saved
         ctx.save_for_backward(latent, Rd, T.detach().float())
         hit = saved["flags"].bitwise_and(1).bool()
@@ -114,8 +125,11 @@ class _RenderDepthFn(torch.autograd.Function):
         scr = ren._scratch()
         ws = _abi.Workspace()
         for name in _abi.WS_FIELDS:
+            if name == "mask_cap":
+                continue
             t = ctx.saved.get(name, scr.get(name))
             setattr(ws, name, t.data_ptr() if t is not None else None)
+        ws.mask_cap = ctx.mask_cap
         pyr = opts["kind"] == "pyramid_recursive"
         gZ = gZ.contiguous().float() if (gZ is not None and opts["want_depth_grad"]) else None
         gM = gM.contiguous().float() if (gM is not None and opts["want_mask_grad"]) else None
@@ -159,7 +173,7 @@ class SDFRenderer(object):
     def __init__(self, decoder, intrinsic, img_hw=None, transform_matrix=None, march_step=50, buffer_size=5,
                  ray_marching_ratio=1.5, use_depth2normal=False, max_sample_dist=0.2, radius=1.0, threshold=5e-5,
                  scale_list=[4, 2, 1], march_step_list=[3, 3, -1], use_gpu=True, is_eval=True, engine=None,
-                 rows=None, screen=None, screen_tpred=0.30, screen_ext_margin=0.04):
+                 rows=None, screen=None, screen_tpred=0.30, screen_ext_margin=0.04, mask_cache=None, mask_rows_per_ray=9.0):
         # renderer.py:13-59
         self.decoder = decoder
         if use_gpu and torch.cuda.device_count() == 0:
@@ -211,13 +225,18 @@ class SDFRenderer(object):
         # decoder-row counters for roofline accounting: forward rows cost F flop, gradient rows (normal / backward
         # replay: forward + transposed chain) cost 2F
         self.rows_evaluated = torch.zeros(1, device=self.device, dtype=torch.int64)
-        self.rows_grad = torch.zeros(1, device=self.device, dtype=torch.int64)
+        # [0] gradient rows evaluated as forward + transposed chain (2F: normals, full backward replay),
+        # [1] backward rows replayed from the mask cache (transposed chain only, F)
+        self.rows_grad = torch.zeros(2, device=self.device, dtype=torch.int64)
         # 128-row tile programs of the forward launches evaluated with [one fp16 pass, three split-precision passes]
         self.tile_counters = torch.zeros(2, device=self.device, dtype=torch.int64)
         # two-tier precision of the march (dist_march_t.screen): on unless switched off here or by DIST_SCREEN=0
         self.screen = (os.environ.get("DIST_SCREEN", "1") != "0") if screen is None else bool(screen)
         self.screen_tpred = float(os.environ.get("DIST_SCREEN_TPRED", screen_tpred))
         self.screen_ext_margin = float(os.environ.get("DIST_SCREEN_EXT", screen_ext_margin))
+        # ReLU-mask cache for the backward (dist_workspace_t.mask_buf): on with the two precision tiers unless switched off
+        self.mask_cache = (os.environ.get("DIST_MASK_CACHE", "1") != "0") if mask_cache is None else bool(mask_cache)
+        self.mask_rows_per_ray = float(mask_rows_per_ray)
         self._homo_calib = None
         self._calib_map = None
         self._scr = None
@@ -348,7 +367,7 @@ class SDFRenderer(object):
             (h1, w1), (h2, w2) = self._coarse_dims()
             npc = (h1 * w1 + h2 * w2) * self.n_views
             self._scr["pyr_f"] = torch.empty(23 * npc, device=self.device, dtype=torch.float32)
-            self._scr["pyr_i"] = torch.empty(npc + 8, device=self.device, dtype=torch.int32)
+            self._scr["pyr_i"] = torch.empty(4 * npc + 8, device=self.device, dtype=torch.int32)
             self._scr["pyr_b"] = torch.empty(npc, device=self.device, dtype=torch.uint8)
         if self._scr is None:
             P, dev = self.P, self.device
@@ -371,6 +390,11 @@ class SDFRenderer(object):
                 # two-tier precision: per-half-tile one-pass flags, the rays' previous sdf
                 "seg_approx": torch.zeros(2 * SEG // 64, device=dev, dtype=torch.uint8), "sprev": torch.empty(P, **f32),
             }
+            # mask cache: per-step slot bases, and the backward's list of rows replayed from the cache
+            n_b = P * self.buffer_size
+            self._scr.update(mask_base=torch.zeros(self.march_step + 3, **i32), bm_row=torch.empty(n_b, **i32),
+                             bm_slot=torch.empty(n_b, **i32), bm_sdf=torch.empty(n_b, **f32), bm_coef=torch.empty(n_b, **f32),
+                             bm_dpts=torch.empty(n_b, 3, **f32), bm_cnt=torch.empty(1, **i32))
             # the exact re-query rows of the forward pass live in the backward replay scratch (free until backward)
             self._scr.update(rq_idx=self._scr["b_row"], rq_pts=self._scr["b_pts"], rq_sdf=self._scr["b_coef"],
                              rq_cnt=self._scr["b_cnt"])

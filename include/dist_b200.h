@@ -157,7 +157,7 @@ typedef struct dist_workspace {
   uint8_t* top_lvl;  /* [B][P] bits 0-1: pyramid level the sample was taken at (0 = this ray; 1, 2 = parent / grandparent
                         ray); bit 7: the recorded sdf is a one-pass value; bit 6: it was re-queried at full precision */
   /* DIST_MARCH_PYRAMID only (renderer.py:713-805).  With (w1,h1) = ceil((w,h)/2), (w2,h2) = ceil((w1,h1)/2),
-   * P1 = w1*h1, P2 = w2*h2:  pyr_f: 23*(P1+P2) floats, pyr_i: (P1+P2)+8 int32, pyr_b: (P1+P2) bytes. */
+   * P1 = w1*h1, P2 = w2*h2:  pyr_f: 23*(P1+P2) floats, pyr_i: 4*(P1+P2)+8 int32, pyr_b: (P1+P2) bytes. */
   float* pyr_f;      /* (all three scale with n_views) */
   int32_t* pyr_i;
   uint8_t* pyr_b;
@@ -171,8 +171,23 @@ typedef struct dist_workspace {
   float* rq_pts;        /* [P*B][3] */
   float* rq_sdf;        /* [P*B] */
   int32_t* rq_cnt;      /* [1] */
+  /* ReLU-mask cache (NULL: off; needs dist_march_t.screen): the forward records, for every march / re-query row evaluated at
+   * full precision, the sign bits of all hidden layers (one 32-bit word per layer and 32-feature block) in
+   * mask_buf[16 * (n_layers - 1)][mask_cap]; a selected sample remembers its slot in top_slot[B][P] (-1: none), and
+   * dist_render_depth_bwd replays such samples with the transposed chain alone (no forward recomputation).  A slot is
+   * mask_base[s] + (row index in segment 2 of step s); mask_base ([march_step + 3] int32) is maintained on the device. */
+  uint32_t* mask_buf;
+  int32_t* mask_base;
+  int32_t* top_slot;
+  int32_t* bm_row;      /* [P*B] backward scratch of the rows replayed from the mask cache: pixel * DIST_MAX_BUFFER + slot ... */
+  int32_t* bm_slot;     /* [P*B] ... their mask slots */
+  float* bm_sdf;        /* [P*B] ... their recorded decoder outputs */
+  float* bm_coef;       /* [P*B] ... their upstream coefficients */
+  float* bm_dpts;       /* [P*B][3] ... d/d point out */
+  int32_t* bm_cnt;      /* [1] */
   unsigned long long* tile_counters; /* optional [2], accumulated: 128-row tile programs evaluated with one fp16 pass /
                            with three (a gradient tile counts two programs: forward + transposed chain) */
+  int64_t mask_cap;   /* row slots of mask_buf */
   int32_t* view_stat; /* [n_views][4] per-view bookkeeping, zeroed by dist_render_depth_fwd: [0] rays alive at step 0
                          (0 <=> the reference raises 'No valid depth', renderer.py:214), [1] march steps the view
                          executed before its early break (renderer.py:562), [2] float bits of the largest coarse-level
@@ -217,6 +232,18 @@ int dist_decoder_forward_tiers(const dist_net_t* net, const float* points, int64
                                int64_t exact_offset, float screen_thresh, float* sdf, uint8_t* seg_approx,
                                unsigned long long* tile_counters, void* stream);
 
+/* Mask cache of the tensor-core engine, exposed for tests (the renderer uses it through dist_workspace_t.mask_buf):
+ * dist_decoder_forward_masks = dist_decoder_forward (three passes, no clamp) that also records the ReLU sign bits of every
+ * hidden layer of row i at slot mask_base + i of mask_buf[16 * (n_layers - 1)][mask_cap];
+ * dist_decoder_backward_masked = dist_decoder_backward for rows given by (mask slot, recorded decoder output, coefficient)
+ * instead of points: the transposed chain alone, no forward recomputation (what the autograd backward of the reference
+ * does with its saved activations, renderer.py:386,415). */
+int dist_decoder_forward_masks(const dist_net_t* net, const float* points, int64_t n, float* sdf, uint32_t* mask_buf,
+                               int64_t mask_cap, int64_t mask_base, void* stream);
+int dist_decoder_backward_masked(const dist_net_t* net, const int32_t* slots, const float* sdf_in, const float* coef, int64_t n,
+                                 float clamp_dist, const uint32_t* mask_buf, int64_t mask_cap, float* dpoints, float* acc0,
+                                 float* accl, void* stream);
+
 /* grad[i] = d clamp(sdf)/d xyz at points[i]; sdf (optional) receives the clamped value.
  * Replaces decode_sdf_gradient (decoder_utils.py:76-92). */
 int dist_decoder_input_grad(const dist_net_t* net, int engine, const float* points, int64_t n_host,
@@ -254,7 +281,9 @@ int dist_render_normal_fwd(const dist_net_t* net, int engine, const dist_camera_
  * d_ray[3][P] (gradient w.r.t. camera centre and per-pixel unit ray, for the host-side camera chain).
  * Either gZ or gM may be NULL.  scratch_* hold the compacted replay rows: rows up to P*buffer_size.
  * d_ray_coarse ([3][P1] then [3][P2], DIST_MARCH_PYRAMID with camera gradients only, else NULL): gradient w.r.t. the
- * unit rays of the 1/2- and 1/4-resolution pixel centres for samples taken on parent rays. */
+ * unit rays of the 1/2- and 1/4-resolution pixel centres for samples taken on parent rays.
+ * rows_evaluated (optional): int64[2] counters, [0] += rows replayed in full (forward + transposed chain, 2F flop each),
+ * [1] += rows replayed from the mask cache (transposed chain only, F flop each). */
 int dist_render_depth_bwd(const dist_net_t* net, int engine, const dist_camera_t* cam, const dist_march_t* mp,
                           const dist_workspace_t* ws, const float* gZ, const float* gM, float* acc0, float* accl,
                           float* d_cam_pos, float* d_ray, float* d_ray_coarse, int32_t* scratch_row_pix, float* scratch_pts,

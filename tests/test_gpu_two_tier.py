@@ -117,3 +117,86 @@ def test_screen_can_be_disabled_and_is_off_for_simt():
     r1 = pkg.SDFRenderer(dec, K, img_hw=(64, 64), engine="tc", screen=False)
     r1.render(lat, R, T, ray_marching_type="recursive", no_grad=True)
     assert r1.tile_counters[0].item() == 0 and r1.tile_counters[1].item() > 0
+
+
+def test_mask_cache_kernels():
+    """Mask cache (csrc/mlp_tc.cu): a forward launch records the ReLU sign bits of every hidden layer; the backward replay
+    from those bits (mode 3: transposed chain only) equals the full replay (mode 2: forward + transposed chain)."""
+    lib, st = abi.lib(), torch.cuda.current_stream().cuda_stream
+    dec = gu.gpu_decoder("B")
+    plan = plan_mod.plan_for(dec)
+    tc.prepare(plan)
+    lat = synth.make_latent().cuda()
+    g = torch.Generator().manual_seed(8)
+    n = 128 * 37 + 19
+    pts = ((torch.rand(n, 3, generator=g) - 0.5) * 1.4).cuda()
+    coef = torch.randn(n, generator=g).cuda()
+    b0, bl, _ = plan.fold(lat, st)
+    bl_tc = bl * tc.S_ACT
+    net = plan.c_net(b0, bl, bl_tc)
+    words, cap, base = 16 * (plan.n_layers - 1), 128 * 64, 128 * 3
+    masks = torch.zeros(words * cap, device="cuda", dtype=torch.int32)
+    sdf = torch.empty(n, device="cuda")
+    abi.check(lib.dist_decoder_forward_masks(net, abi.ptr(pts), n, abi.ptr(sdf), abi.ptr(masks), cap, base, st))
+    exact = pkg.decode_sdf(dec, lat, pts, clamp_dist=None, no_grad=True, engine="tc").reshape(-1)
+    assert torch.equal(sdf, exact)
+    # the recorded bits against the module's eager layers (a pre-activation within rounding of zero may differ)
+    acts = []
+    hooks = [getattr(dec, "lin%d" % l).register_forward_hook(lambda m, i, o: acts.append(o)) for l in range(plan.n_layers - 1)]
+    with torch.no_grad():
+        dec._inference_torch(torch.cat([lat.expand(n, -1), pts], 1))
+    for h in hooks:
+        h.remove()
+    mv = masks.view(words, cap)[:, base:base + n]
+    bad = tot = 0
+    for l, a in enumerate(acts):
+        width = a.shape[1]
+        bits = (a > 0).to(torch.int64)
+        for kb in range((width + 31) // 32):
+            blk = bits[:, 32 * kb:32 * kb + 32]
+            word = (blk << torch.arange(blk.shape[1], device="cuda")).sum(1)
+            got = mv[l * 16 + kb].to(torch.int64) & 0xFFFFFFFF
+            valid = (1 << blk.shape[1]) - 1
+            diff = (got ^ word) & valid
+            bad += int(sum(((diff >> j) & 1).sum() for j in range(blk.shape[1])))
+            tot += blk.numel()
+    assert bad <= max(4, 2e-5 * tot), (bad, tot)
+    # backward from the cache == full replay
+    d_ref, a0_ref, al_ref = torch.empty(n, 3, device="cuda"), torch.zeros(plan.bias[0].numel(), device="cuda"), \
+        torch.zeros(plan.bias[plan.latent_in].numel(), device="cuda")
+    abi.check(lib.dist_decoder_backward(net, abi.ENGINE_TC, abi.ptr(pts), abi.ptr(coef), None, n, None, 0.0, abi.ptr(d_ref),
+                                        abi.ptr(a0_ref), abi.ptr(al_ref), st))
+    slots = (base + torch.arange(n, device="cuda")).to(torch.int32)
+    d_m, a0_m, al_m = torch.empty(n, 3, device="cuda"), torch.zeros_like(a0_ref), torch.zeros_like(al_ref)
+    abi.check(lib.dist_decoder_backward_masked(net, abi.ptr(slots), abi.ptr(sdf), abi.ptr(coef), n, 0.0, abi.ptr(masks), cap,
+                                               abi.ptr(d_m), abi.ptr(a0_m), abi.ptr(al_m), st))
+    torch.cuda.synchronize()
+    assert torch.equal(d_m, d_ref)
+    assert gu.rel(a0_m, a0_ref) < 1e-5 and gu.rel(al_m, al_ref) < 1e-5
+    del b0, bl, bl_tc
+
+
+@pytest.mark.parametrize("kind", ["recursive", "pyramid_recursive"])
+def test_mask_cache_backward_equals_full_replay(kind):
+    """render() + backward with the mask cache (default) and without: identical maps, gradients equal to rounding of the
+    atomics, and the cached path really carries most of the replay rows."""
+    dec = gu.gpu_decoder("B")
+    hw = (128, 128)
+    K, R, T = cases.camera(("lookat", 40.0, 25.0, 2.5, 1.2 * 2.5 / 1.6), hw)
+    res = []
+    for mc in (True, False):
+        ren = pkg.SDFRenderer(dec, K, img_hw=hw, march_step=50, buffer_size=5, engine="tc", mask_cache=mc)
+        lat = synth.make_latent().cuda().requires_grad_(True)
+        Rg, Tg = R.cuda().requires_grad_(True), T.cuda().requires_grad_(True)
+        out = ren.render(lat, Rg, Tg, ray_marching_type=kind)
+        cases.scalar_loss(out).backward()
+        torch.cuda.synchronize()
+        res.append(([o.detach() for o in out], (lat.grad, Rg.grad, Tg.grad), int(ren._scr["bm_cnt"].item()) if mc else 0,
+                    int(ren._scr["b_cnt"].item())))
+    (o1, g1, cached, rest), (o2, g2, _, full) = res
+    for a, b in zip(o1, o2):
+        assert torch.equal(a, b)
+    for a, b in zip(g1, g2):
+        assert gu.rel(a, b) < 1e-5
+    print(kind, "replay rows from the cache", cached, "full replay", rest, "(without the cache:", full, ")")
+    assert cached + rest == full and cached > 0.8 * full
