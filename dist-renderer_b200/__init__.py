@@ -8,6 +8,8 @@ Public surface (mirrors the reference's names):
   decode_sdf, decode_sdf_gradient  core/utils/decoder_utils.py:53,76
   decode_color                     core/utils/decoder_utils.py:94
   Decoder, load_decoder            core/graph/deep_sdf_decoder.py:18, core/utils/decoder_utils.py:7
+  evaluation.Evaluator, evaluation.latent_vec_to_points, evaluation.compute_chamfer_distance
+                                   core/evaluation/evaluator.py:8, transforms.py:13, eval_func.py:5
 """
 from .decoder import Decoder, load_decoder  # noqa: F401
 from .functional import decode_sdf, decode_sdf_gradient, decode_color  # noqa: F401

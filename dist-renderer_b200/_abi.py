@@ -9,7 +9,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libdist_b200.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_LAYERS = 16
 MAX_WIDTH = 512
 MAX_BUFFER = 8
@@ -90,6 +90,14 @@ PROTOTYPES = {
     "dist_warp_loss_fwd": (C.c_int, [C.POINTER(Camera), C.POINTER(C.c_float)] + [C.c_void_p] * 7 + [C.c_float] +
                            [C.c_void_p] * 6),
     "dist_warp_loss_bwd": (C.c_int, [C.POINTER(Camera), C.POINTER(C.c_float)] + [C.c_void_p] * 13),
+    "dist_scan_scratch_elems": (C.c_int64, [C.c_int64]),
+    "dist_mc_count": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float] + [C.c_void_p] * 5),
+    "dist_mc_emit": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_float)] +
+                     [C.c_void_p] * 5),
+    "dist_tri_area_scan": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64] + [C.c_void_p] * 4),
+    "dist_surface_sample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64] +
+                            [C.c_void_p] * 3),
+    "dist_nearest_sqdist": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64] + [C.c_void_p] * 4),
 }
 
 _lib = None

@@ -12,20 +12,30 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"] + \
     os.environ.get("DIST_EXTRA_NVCC_FLAGS", "").split()      # e.g. -DDIST_TC_TIMELINE for the per-layer timeline of mlp_tc.cu
 # march.cu mirrors PyTorch's separately-rounded elementwise ops: no FMA contraction there
-SOURCES = {"abi.cu": [], "warp.cu": [], "march.cu": ["-fmad=false"], "mlp_simt.cu": ["-Xptxas", "-v"], "mlp_tc.cu": ["-Xptxas", "-v"]}
+SOURCES = {"abi.cu": [], "warp.cu": [], "mesh.cu": ["-fmad=false"], "march.cu": ["-fmad=false"], "mlp_simt.cu": ["-Xptxas", "-v"], "mlp_tc.cu": ["-Xptxas", "-v"]}
 
 
 def _stamp():
     h = hashlib.sha1()
     for root in (CSRC, os.path.join(HERE, "..", "include")):
         for f in sorted(os.listdir(root)):
-            if f.endswith((".cu", ".cuh", ".h")):
+            if f.endswith((".cu", ".cuh", ".h", ".inc")):
                 h.update(open(os.path.join(root, f), "rb").read())
     h.update(" ".join(ARCH + COMMON).encode())
     return h.hexdigest()
 
 
+def _mc_tables():
+    """csrc/mc_tables.inc (marching-cubes case tables) is derived by mc_tables.py; (re)write it before hashing the sources."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_dist_mc_tables", os.path.join(HERE, "mc_tables.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    mod.write_header(os.path.join(CSRC, "mc_tables.inc"))
+
+
 def build(force=False, verbose=False):
+    _mc_tables()
     stamp_file = LIB + ".stamp"
     stamp = _stamp()
     if not force and os.path.isfile(LIB) and os.path.isfile(stamp_file) and open(stamp_file).read() == stamp:

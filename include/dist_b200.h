@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define DIST_ABI_VERSION 2
+#define DIST_ABI_VERSION 3
 #define DIST_MAX_LAYERS 16
 #define DIST_MAX_WIDTH 512
 #define DIST_MAX_BUFFER 8      /* max buffer_size (samples kept per ray) */
@@ -308,6 +308,40 @@ int dist_warp_loss_fwd(const dist_camera_t* cam1, const float* K_host, const flo
 int dist_warp_loss_bwd(const dist_camera_t* cam1, const float* K_host, const float* R2, const float* T2, const float* Zdepth1,
                        const uint8_t* keep, const float* img1, const float* img2, const float* gscale, float* dZdepth1,
                        float* d_ray1, float* d_cam_pos1, float* dR2, float* dT2, void* stream);
+
+/* ---- mesh extraction: device replacements for the host half of latent_vec_to_points -------------
+ * Reference: core/evaluation/create_mesh.py:144-175 (skimage.measure.marching_cubes_lewiner on a host copy of the grid),
+ * core/evaluation/transforms.py:8-32 (.ply on disk -> trimesh.sample.sample_surface), core/evaluation/eval_func.py:5-39
+ * (scipy cKDTree chamfer).  All pointers are device pointers unless they say _host; nothing is allocated inside.
+ *
+ * Marching cubes over vol[n0][n1][n2] (fp32, axis 2 fastest), inside = value < level.  Two calls because the output size
+ * is data dependent:
+ *   dist_mc_count  fills scan[M] (M = n0*n1*n2; low 32 bits = index of the grid point's first vertex, high 32 bits = index
+ *                  of its cube's first triangle), mask[M] (which of the point's +axis edges carry a vertex) and
+ *                  totals[0] = n_vertices + (n_triangles << 32); scratch holds dist_scan_scratch_elems(M) int64.
+ *   dist_mc_emit   writes verts[n_vertices][3] = origin_host + spacing_host * (grid index + t) and faces[n_triangles][3]
+ *                  (vertex order: grid point, then axis; face order: cube, then the case table's order; normals point
+ *                  towards larger values).  Case table and conventions: dist-renderer_b200/mc_tables.py. */
+int64_t dist_scan_scratch_elems(int64_t n);
+int dist_mc_count(const float* vol, int n0, int n1, int n2, float level, int64_t* scan, uint8_t* mask, int64_t* scratch,
+                  int64_t* totals, void* stream);
+int dist_mc_emit(const float* vol, int n0, int n1, int n2, float level, const float* origin_host, const float* spacing_host,
+                 const int64_t* scan, const uint8_t* mask, float* verts, int32_t* faces, void* stream);
+
+/* Area-weighted surface sampling (trimesh.sample.sample_surface's scheme).  dist_tri_area_scan: cum[n_faces] = exclusive
+ * prefix sums (fp64) of the fp32 triangle areas, total[0] = their sum; scratch holds dist_scan_scratch_elems(n_faces)
+ * doubles.  dist_surface_sample: for uniforms u[count][3] in [0,1), u[.][0] picks the face whose cumulative-area interval
+ * holds u*total, (u[.][1], u[.][2]) the point (reflected when their sum exceeds 1); points[count][3], face_index[count]
+ * (may be NULL). */
+int dist_tri_area_scan(const float* verts, const int32_t* faces, int64_t n_faces, double* cum, double* scratch, double* total,
+                       void* stream);
+int dist_surface_sample(const float* verts, const int32_t* faces, int64_t n_faces, const double* cum, const double* total,
+                        const float* u, int64_t count, float* points, int32_t* face_index, void* stream);
+
+/* d2[i] = squared distance from query[i] to its nearest point of ref (fp32, brute force), index[i] = that point (may be
+ * NULL); best[n_query] is uint64 scratch.  cKDTree(ref).query(query) of eval_func.py:10-11,19-20. */
+int dist_nearest_sqdist(const float* ref, int64_t n_ref, const float* query, int64_t n_query, uint64_t* best, float* d2,
+                        int32_t* index, void* stream);
 
 #ifdef __cplusplus
 }

@@ -3,6 +3,7 @@
 Run in the build container (needs /root/reference):   python oracle/make_golden.py            (small cases)
                                                        python oracle/make_golden.py --flags    (gradient flags)
                                                        python oracle/make_golden.py --big      (BASELINE sizes; ~20 min)
+                                                       python oracle/make_golden.py --chamfer  (eval_func.py outputs)
 Each fixture holds the outputs of the unmodified reference `SDFRenderer.render` (depth, normal, mask, min_sdf),
 the gradients of tests/cases.scalar_loss w.r.t. latent / R / T, and a checksum of the seeded decoder weights
 the recipe regenerates.  `decoder_points.npz` pins decode_sdf / decode_sdf_gradient on random points.
@@ -126,7 +127,22 @@ def flag_fixtures():
     print("silhouette_48 hits", int(vm.sum()))
 
 
+def chamfer_fixture():
+    """Outputs of the reference's core/evaluation/eval_func.py on the seeded point sets of tests/test_mesh_cpu.py."""
+    EF = ref_shim.load_eval_func()
+    rng = np.random.default_rng(7)
+    a = rng.standard_normal((3000, 3)) * 0.3
+    b = rng.standard_normal((2500, 3)) * 0.3 + 0.05
+    np.savez_compressed(os.path.join(cases.GOLDEN_DIR, "chamfer.npz"), a=a, b=b, sq=EF.compute_chamfer_distance(a, b),
+                        lin=EF.compute_chamfer_distance(a, b, use_square_dist=False),
+                        sep=np.array(EF.compute_chamfer_distance_separate(a, b)))
+    print("chamfer", EF.compute_chamfer_distance(a, b))
+
+
 def main():
+    if "--chamfer" in sys.argv:
+        os.makedirs(cases.GOLDEN_DIR, exist_ok=True)
+        return chamfer_fixture()
     if "--big" in sys.argv:              # minutes of CPU per case: written separately from the small fixtures
         os.makedirs(cases.GOLDEN_DIR, exist_ok=True)
         return big_fixtures([a for a in sys.argv[1:] if not a.startswith("--")])

@@ -143,6 +143,15 @@ def load_create_mesh():
     return _loaded["CM"]
 
 
+def load_eval_func():
+    """The reference's core/evaluation/eval_func.py as it is (numpy + scipy cKDTree, both installed here)."""
+    if "EF" not in _loaded:
+        load()
+        _stub("core.evaluation", "/core/evaluation")
+        _loaded["EF"] = _load("core.evaluation.eval_func", "core/evaluation/eval_func.py")
+    return _loaded["EF"]
+
+
 def load():
     """Returns (renderer_module, decoder_utils_module, DecoderClass) of the reference."""
     if _loaded:

@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol(libpath):
     lib = ctypes.CDLL(libpath)
     for n in _declared_functions():
         assert hasattr(lib, n), "missing symbol " + n
-    assert lib.dist_abi_version() == importlib.import_module("dist-renderer_b200._abi").ABI_VERSION == 2
+    assert lib.dist_abi_version() == importlib.import_module("dist-renderer_b200._abi").ABI_VERSION == 3
 
 
 def test_python_binding_matches_header(libpath):
