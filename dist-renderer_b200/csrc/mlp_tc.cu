@@ -93,6 +93,7 @@ struct TcParams {
   float sA, sD;                    // activation / gradient operand scales
   int first_append;                // layer 0's output gets xyz appended (latent_in == 1)
   int dbg;                         // diagnostics (DIST_TC_DEBUG), see the file header
+  int stage_rows;                  // tensor-map rows per 16 KB weight stage (STAGE_BYTES / bytes per box row)
 };
 
 struct TcIO {
@@ -338,7 +339,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
                 const uint32_t dst = sbase + OFF_W + slot * STAGE_BYTES;
                 const uint32_t bar = W_FULL(slot) & bar_leader_mask;
                 if (exact) {
-                  const int row = ((sb + s) * 2 + (int)rank) * (STAGE_BYTES / 128);
+                  const int row = ((sb + s) * 2 + (int)rank) * P.stage_rows;
                   asm volatile(
                       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
                           "r"(dst), "l"(&tmap), "r"(bar), "r"(0), "r"(row)
@@ -346,7 +347,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
                 } else {
 #pragma unroll
                   for (int c = 0; c < 2; ++c) {
-                    const int row = ((sb + 2 * s + c) * 2 + (int)rank) * (STAGE_BYTES / 128);
+                    const int row = ((sb + 2 * s + c) * 2 + (int)rank) * P.stage_rows;
                     asm volatile(
                         "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
                             "r"(dst + c * (STAGE_BYTES / 2)), "l"(&tmap_hi), "r"(bar), "r"(0), "r"(row)
@@ -1164,12 +1165,17 @@ int mlp_tc_launch(const dist_net_t* net, const NetDev& nd, int mode, const MlpAr
   static long long* dbg_buf = nullptr;
   if (P.dbg & 4) { if (!dbg_buf) { cudaMalloc(&dbg_buf, 4096); cudaMemset(dbg_buf, 0, 4096); } io.dbg_out = dbg_buf; }
 
-  // tensor map over the blob: rows of 128 B; one box = one 16 KB stage of one CTA
+  // tensor map over the blob, which is laid out stage by stage: one box = one contiguous 16 KB stage of one CTA.  The box row
+  // length only decides how many row requests the TMA unit issues per stage (DIST_TC_BOXROW = 128/256/512 bytes: measured
+  // identical, profiles/r2_tc_summary.md -- the weight stream is not limited by TMA request issue)
+  static const int boxrow = [] { const char* e = getenv("DIST_TC_BOXROW"); int v = e ? atoi(e) : 128;
+                                 return (v == 128 || v == 256 || v == 512) ? v : 128; }();
+  P.stage_rows = STAGE_BYTES / boxrow;
   CUtensorMap tmap;
-  const cuuint64_t rows = (cuuint64_t)(net->tc_blob_bytes / 128);
-  const cuuint64_t gdim[2] = {64, rows};
-  const cuuint64_t gstr[1] = {128};
-  const cuuint32_t box[2] = {64, STAGE_BYTES / 128};
+  const cuuint64_t rows = (cuuint64_t)(net->tc_blob_bytes / boxrow);
+  const cuuint64_t gdim[2] = {(cuuint64_t)(boxrow / 2), rows};
+  const cuuint64_t gstr[1] = {(cuuint64_t)boxrow};
+  const cuuint32_t box[2] = {(cuuint32_t)(boxrow / 2), (cuuint32_t)(STAGE_BYTES / boxrow)};
   const cuuint32_t estr[2] = {1, 1};
   CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(net->tc_blob), gdim, gstr, box, estr,
                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -1177,7 +1183,7 @@ int mlp_tc_launch(const dist_net_t* net, const NetDev& nd, int mode, const MlpAr
   if (cr != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)cr); return DIST_E_CUDA; }
   // same blob, boxes of the first 8 KB ([hi]) of a stage only: what a one-pass tile fetches
   CUtensorMap tmap_hi;
-  const cuuint32_t box_hi[2] = {64, STAGE_BYTES / 256};
+  const cuuint32_t box_hi[2] = {(cuuint32_t)(boxrow / 2), (cuuint32_t)(STAGE_BYTES / 2 / boxrow)};
   cr = encode(&tmap_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(net->tc_blob), gdim, gstr, box_hi, estr,
               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
