@@ -58,6 +58,7 @@ constexpr int NST = 6;                 // weight ring stages
 constexpr int STAGE_BYTES = 16384;     // per CTA: [hi 8 KB][lo 8 KB]
 constexpr int OFF_AHI = 0, OFF_ALO = 65536, OFF_W = 131072;
 constexpr int OFF_BAR = OFF_W + NST * STAGE_BYTES;   // 229376
+constexpr int OFF_HDR = OFF_BAR + 448;               // three int64: row counts of the two segments, mask-cache base
 constexpr int OFF_PART = OFF_BAR + 512;              // per-row partial sums [64][8] (8 threads share a row)
 constexpr int OFF_ROWD = OFF_PART + 2048;            // per-row scalar [64]
 constexpr int OFF_FAIL = OFF_ROWD + 256;             // two-tier precision: [near flag u32][pad][fail bitmap, FAIL_WORDS u32]
@@ -228,15 +229,25 @@ template <int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
 mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_hi, const TcParams P, const TcIO io) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  // rows: segment 1 = [0, n1), segment 2 = [seg2_offset, seg2_offset + n2) (seg2_offset a multiple of 128)
-  const int64_t n1 = io.n_dev ? (int64_t)*io.n_dev : io.n_host;
-  const int64_t n2 = io.n2_dev ? (int64_t)*io.n2_dev : io.n2_host;
+  // rows: segment 1 = [0, n1), segment 2 = [seg2_offset, seg2_offset + n2) (seg2_offset a multiple of 128).
+  // Device-side counts are read by ONE thread per CTA and handed round through shared memory: 20 warps x 148 CTAs loading the
+  // same word at kernel start queue up on one L2 sector.
+  volatile int64_t* hdr = reinterpret_cast<volatile int64_t*>(smem + OFF_HDR);
+  if (threadIdx.x == 0) {
+    const int64_t v0 = io.n_dev ? (int64_t)*io.n_dev : io.n_host;          // three independent loads in flight
+    const int64_t v1 = io.n2_dev ? (int64_t)*io.n2_dev : io.n2_host;
+    const int64_t v2 = (MODE == 0 && io.mask_buf) ? (io.mask_base_dev ? (int64_t)*io.mask_base_dev : io.mask_base_host) : -1;
+    hdr[0] = v0; hdr[1] = v1; hdr[2] = v2;
+  }
+  __syncthreads();
+  const int64_t n1 = hdr[0], n2 = hdr[1];
   const int64_t n = n1 + n2;
   if (n <= 0) return;
   const uint32_t rank = cluster_ctarank();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
   const int64_t tiles1 = (n1 + 127) / 128, n_tiles = tiles1 + (n2 + 127) / 128;
+  if ((blockIdx.x >> 1) >= n_tiles) return;     // a cluster without a tile (grid sized for a device-side row count): both CTAs leave
   auto row0_of = [&](int64_t t) -> int64_t { return (t < tiles1) ? t * 128 : io.seg2_offset + (t - tiles1) * 128; };
   auto lim_of = [&](int64_t t) -> int64_t { return (t < tiles1) ? n1 : io.seg2_offset + n2; };
   if (blockIdx.x == 0 && tid == 0 && io.rows_evaluated)
@@ -245,7 +256,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
   // bits of all hidden layers (one word per layer and 32-feature block, 512 B per row for the 8x512 network) at slot
   // mask_base + (index of the row among those rows).  The backward replay (MODE 3) then runs the transposed chain alone:
   // the forward half of MODE 2 only existed to recompute these bits.
-  const int64_t mask_base = (MODE == 0 && io.mask_buf) ? (io.mask_base_dev ? (int64_t)*io.mask_base_dev : io.mask_base_host) : -1;
+  const int64_t mask_base = hdr[2];
 
   long long dbg_c0 = 0, dbg_t0 = 0;
   if (io.dbg_out && blockIdx.x == 0 && tid == 0) { dbg_c0 = clock64(); asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0)); }

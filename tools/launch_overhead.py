@@ -23,22 +23,30 @@ sdf = torch.empty(N, device="cuda")
 ndev = torch.zeros(1, dtype=torch.int32, device="cuda")
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 wave = 128 * 74
-for label, use_dev in (("n_host", False), ("n_dev (grid sized for 262144 rows)", True)):
-    print(label)
-    for n in (1, 128, wave // 2, wave, wave + 128, 2 * wave, 3 * wave, 4 * wave, 8 * wave, 16 * wave, N):
-        ndev.fill_(n)
-        reps = 40 if n < 100000 else 10
-        def go():
-            if use_dev:
-                _abi.check(lib.dist_decoder_forward(net, eng, _abi.ptr(pts), N, _abi.ptr(ndev), 0.1, _abi.ptr(sdf), st))
-            else:
-                _abi.check(lib.dist_decoder_forward(net, eng, _abi.ptr(pts), n, None, 0.1, _abi.ptr(sdf), st))
-        for _ in range(3):
-            go()
-        torch.cuda.synchronize()
-        e0.record()
-        for _ in range(reps):
-            go()
-        e1.record(); torch.cuda.synchronize()
-        us = e0.elapsed_time(e1) / reps * 1e3
-        print("  n=%7d (%.2f waves): %8.1f us/launch" % (n, n / wave, us))
+def measure(n, use_dev):
+    ndev.fill_(n)
+    reps = 40 if n < 100000 else 10
+
+    def go():
+        if use_dev:
+            _abi.check(lib.dist_decoder_forward(net, eng, _abi.ptr(pts), N, _abi.ptr(ndev), 0.1, _abi.ptr(sdf), st))
+        else:
+            _abi.check(lib.dist_decoder_forward(net, eng, _abi.ptr(pts), n, None, 0.1, _abi.ptr(sdf), st))
+    for _ in range(3):
+        go()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        go()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps * 1e3
+
+
+# the two modes alternate (three rounds, best of) so that clock drift over the run does not read as a difference between them
+print("rows (waves): host-side count | device-side count, grid sized for %d rows" % N)
+for n in (1, 128, wave // 2, wave, wave + 128, 2 * wave, 3 * wave, 4 * wave, 8 * wave, 16 * wave, N):
+    best = [1e30, 1e30]
+    for _ in range(3):
+        for k, use_dev in enumerate((False, True)):
+            best[k] = min(best[k], measure(n, use_dev))
+    print("  n=%7d (%5.2f waves): %8.1f us/launch | %8.1f us/launch" % (n, n / wave, best[0], best[1]))
