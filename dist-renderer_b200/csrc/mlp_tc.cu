@@ -567,7 +567,10 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
       if (lane == 0) mbar_arrive_cluster(A_FULL(kc), 0);
     };
     // layer 0 on CUDA cores: A <- split(sA * relu(b0' + W0 xyz)) for this thread's 32-feature blocks
-    auto layer0 = [&](int64_t slot) {
+    // guard_kc32 > 0: the previous tile's LAST layer is still being read by its final MMA pass -- block kb is overwritten
+    // only once A_FREE(kb) of that layer has fired (blocks >= guard_kc32 are not read by it), so this tile's layer 0 runs
+    // underneath the previous tile's last pass instead of after it
+    auto layer0 = [&](int64_t slot, int guard_kc32) {
       const int kblocks = P.L[0].kc32;                          // 32-feature blocks the first MMA layer consumes
       const int nh0 = (P.N0 + 255) >> 8;
       for (int h = 0; h < nh0; ++h) {
@@ -575,6 +578,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
         if (kb >= kblocks) continue;
         const int f0 = 32 * kb;
         uint32_t m0 = 0;
+        if (kb < guard_kc32) mbar_wait(A_FREE(kb), (free_phase >> kb) & 1);
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           float x[8];
@@ -627,13 +631,14 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
       if (i + 1 < c1 && grb < n1) { qx = io.points[grb * 3]; qy = io.points[grb * 3 + 1]; qz = io.points[grb * 3 + 2]; }
       else { qx = qy = qz = 0.f; }
     };
-    auto layer0_pair = [&]() {     // layer 0 of both tiles on CUDA cores: hi halves into the two activation regions
+    auto layer0_pair = [&](int guard_kc32) {     // layer 0 of both tiles on CUDA cores: hi halves into the two activation regions
       const int kblocks = P.L[0].kc32;
       const int nh0 = (P.N0 + 255) >> 8;
       for (int h = 0; h < nh0; ++h) {
         const int kb = 8 * h + 4 * q + ch;
         if (kb >= kblocks) continue;
         const int f0 = 32 * kb;
+        if (kb < guard_kc32) mbar_wait(A_FREE(kb), (free_phase >> kb) & 1);      // (see layer0)
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           float xa[8], xb[8];
@@ -700,10 +705,10 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
       if (inext < 0 || MODE == 3) return;
       if (phase == 0 && inext < c1) load_points_pair(inext); else load_point(tile_of(inext));
     };
-    auto start_layer0 = [&](int phase, int inext) {
+    auto start_layer0 = [&](int phase, int inext, int guard_kc32) {
       if (inext < 0) return;
       if (MODE == 3) { seed(tile_of(inext)); return; }
-      if (phase == 0 && inext < c1) layer0_pair(); else layer0(rec_slot(tile_of(inext)));
+      if (phase == 0 && inext < c1) layer0_pair(guard_kc32); else layer0(rec_slot(tile_of(inext)), guard_kc32);
     };
     // the whole forward program of one pair (tiles i and, if has_b, i + 1 of this cluster's list)
     auto run_pair = [&](int i, int inext, bool has_b) {
@@ -723,17 +728,15 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
           d_phase ^= (1u << h);
           tc_fence_after();
         };
-        if (last) {
-          prefetch_points(0, inext);
-          for (int h = 0; h < Lnh; ++h) wait_h(h);      // all MMAs of the pair are complete: both activation regions are free
-          start_layer0(0, inext);
-        }
+        if (last) prefetch_points(0, inext);
         for (int h = 0; h < Lnh; ++h) {
           const int kb = 8 * h + 4 * q + ch;
           const int fb = 32 * kb;
           const bool need_store = !last && kb < kblocks_next;
           const bool process = last ? (fb < LN) : need_store;
-          if (!last) wait_h(h);
+          // last layer: the next tile's layer 0 is written block by block while the final pass still runs (A_FREE guards)
+          if (last && h == Lnh - 1) start_layer0(0, inext, kc32_cur);
+          wait_h(h);
           if (!process) continue;
           const bool interior = (fb + 32 <= LN);
           if (h == 0 && rank == 0 && warp == 4) TL_MARK(8 + m * 4 + 2);
@@ -812,7 +815,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
     for (int phase = 0; phase < 2; ++phase) {
     int i = next_tile(phase, -1);
     prefetch_points(phase, i);
-    start_layer0(phase, i);
+    start_layer0(phase, i, 0);
     while (i >= 0) {
       const int64_t t = tile_of(i);
       const int inext = next_tile(phase, i);
@@ -847,17 +850,20 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
         };
         // the next tile's points are fetched before the wait so that their latency hides behind the last MMAs
         // (px/py/pz of this tile are no longer needed: xyz is only appended in earlier forward layers)
+        // MODE 0 (forward only): the last layer's epilogue does not write A, so the next tile's layer 0 can be written block
+        // by block under the final MMA pass (A_FREE guards, see layer0).  The other modes recycle A after all MMAs are done.
+        constexpr bool EARLY0 = (MODE == 0);
         if (prog_last) prefetch_points(phase, inext);
-        if (prog_last) for (int h = 0; h < Lnh; ++h) wait_half(h);   // all MMAs of the tile done before A is recycled
+        if (prog_last && !EARLY0) for (int h = 0; h < Lnh; ++h) wait_half(h);   // all MMAs of the tile done before A is recycled
 #ifdef DIST_TC_TIMELINE
         const bool dbg_rec = io.dbg_out && cluster_id == 0 && rank == 0 && warp == 4 && lane == 0 && t == cluster_id + n_clusters;
 #else
         const bool dbg_rec = false;
 #endif
-        if (prog_last) {
+        if (prog_last && !EARLY0) {
           // all MMAs of this tile are complete: A is free -> start the next tile's layer 0 before draining D
-          if (MODE != 0) { mk0s[0] = mk[0][0]; mk0s[1] = mk[0][1]; }
-          start_layer0(phase, inext);
+          mk0s[0] = mk[0][0]; mk0s[1] = mk[0][1];
+          start_layer0(phase, inext, 0);
         }
         const int kblocks_next = prog_last ? 0 : P.L[m + 1].kc32;
         // net layer whose ReLU mask gates the values produced here (transposed chain): l-1 with l = 2 n_mma - m
@@ -870,7 +876,8 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
           else if (fwd_last) { process = fb < LN; }
           else if (!prog_last) { need_store = kb < kblocks_next; process = need_store || (Lapp && fb < LN + 3 && fb + 32 > LN); }
           else { process = fb < LN + 3 * Lapp; }
-          if (!prog_last) wait_half(h);       // every epilogue warp waits for each half exactly once per layer
+          if (EARLY0 && prog_last && h == Lnh - 1) start_layer0(phase, inext, kc32_cur);
+          if (!prog_last || EARLY0) wait_half(h);       // every epilogue warp waits for each half exactly once per layer
           if (!process) continue;
           if (dbg_rec && h == 0) io.dbg_out[8 + m * 4 + 2] = clock64();
           float v[32];
