@@ -178,7 +178,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 def pick_threads(synth):
@@ -247,9 +247,24 @@ def ncu_traffic(tc):
         return None
 
 
+_JSON_OUT = None
+
+
+def _emit(line):
+    """The one JSON line of the contract, on the process's ORIGINAL stdout."""
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
-    # NCCL writes its version / INFO lines to stdout by default; stdout carries exactly one JSON line
+    # stdout carries exactly one JSON line: NCCL prints its version banner (and INFO lines) with printf on fd 1 whatever
+    # NCCL_DEBUG_FILE says, so fd 1 is pointed at stderr for the whole run and the JSON goes to a saved copy of the real stdout
+    global _JSON_OUT
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -522,7 +537,7 @@ def main():
             "engine": "tc" if ren.local.plan.tc is not None else "simt", "step_ms": step_ms, "per_rank": per_rank,
         }
         line.update(extras)
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
