@@ -317,10 +317,21 @@ class SDFRenderer(object):
         row0, step, _, grp = self.rows
         return row0 + (local_rows // grp) * step + local_rows % grp
 
+    def _transform_host(self):
+        """Host copy of `transform_matrix` (9 floats for the camera descriptor).  Cached: reading the device tensor back on
+        every call would make each render_depth / render_normal / backward wait for all queued GPU work.  The cache is keyed
+        on the tensor object and its version counter, so assigning or modifying `self.transform_matrix` refreshes it."""
+        tm = self.transform_matrix
+        key = (id(tm), tm._version)
+        if getattr(self, "_tm_host_key", None) != key:
+            self._tm_host = tm.detach().cpu().numpy().astype(np.float32).reshape(-1)
+            self._tm_host_key = key
+        return self._tm_host
+
     def _c_camera(self, R, cam_pos, use_transform=True):
         cam = _abi.Camera()
         Kinv = np.linalg.inv(self.intrinsic).astype(np.float32).reshape(-1)
-        Mn = self.transform_matrix.detach().cpu().numpy().reshape(-1)
+        Mn = self._transform_host()
         M = Mn if use_transform else np.eye(3).reshape(-1)
         for i in range(9):
             cam.Kinv[i], cam.M[i], cam.Mn[i] = float(Kinv[i]), float(M[i]), float(Mn[i])
