@@ -124,3 +124,34 @@ def test_chamfer_oracle_matches_golden():
     assert np.isclose(O.compute_chamfer_distance(a, b), float(g["sq"]), rtol=1e-12)
     assert np.isclose(O.compute_chamfer_distance(a, b, False), float(g["lin"]), rtol=1e-12)
     assert np.allclose(O.compute_chamfer_distance_separate(a, b), g["sep"], rtol=1e-12)
+
+
+def test_write_ply_round_trip(tmp_path):
+    """evaluation.write_ply: binary little-endian, float x/y/z + uchar-counted int32 faces (create_mesh.py:180-198)."""
+    import torch
+    ev = importlib.import_module("dist-renderer_b200.evaluation")
+    cs = mesh_cases.VOLUMES["sphere_ragged"]
+    v, f = O.marching_cubes(cs["vol"](), cs["level"], cs["spacing"], cs["origin"])
+    path = str(tmp_path / "m.ply")
+    ev.write_ply(torch.from_numpy(v), torch.from_numpy(f), path)
+    raw = open(path, "rb").read()
+    head, body = raw.split(b"end_header\n", 1)
+    lines = head.decode("ascii").split("\n")
+    assert lines[0] == "ply" and lines[1] == "format binary_little_endian 1.0"
+    assert "element vertex %d" % len(v) in lines and "element face %d" % len(f) in lines
+    assert "property list uchar int vertex_indices" in lines
+    vv = np.frombuffer(body[:len(v) * 12], dtype="<f4").reshape(-1, 3)
+    rec = np.frombuffer(body[len(v) * 12:], dtype=[("n", "u1"), ("idx", "<i4", (3,))])
+    assert np.array_equal(vv, v) and np.all(rec["n"] == 3) and np.array_equal(rec["idx"], f)
+
+
+def test_evaluation_rejects_cpu_tensors():
+    """No CPU path: the mesh entry points refuse host tensors instead of computing on the host."""
+    import torch
+    ev = importlib.import_module("dist-renderer_b200.evaluation")
+    with pytest.raises(ValueError, match="CUDA"):
+        ev.marching_cubes(torch.zeros(4, 4, 4), 0.0)
+    with pytest.raises(ValueError, match="CUDA"):
+        ev.nearest_sqdist(torch.zeros(4, 3), torch.zeros(2, 3))
+    with pytest.raises(ValueError, match="CUDA"):
+        ev.sample_surface(torch.zeros(3, 3), torch.zeros(1, 3, dtype=torch.int32), 5)
