@@ -489,20 +489,81 @@ __global__ void k_finalize(dist_march_t mp, dist_workspace_t ws, float* Zdepth, 
     nreal = B;
     ws.nreal[lp] = B;
   }
-  {   // the records are an unordered set until here: ascending |sdf| (stable), the minimum to slot 0 (renderer.py:316-319)
-    for (int a = 1; a < B; ++a)
-      for (int b = a; b > 0 && fabsf(ws.top_sdf[(size_t)b * P + lp]) < fabsf(ws.top_sdf[(size_t)(b - 1) * P + lp]); --b) {
-        const size_t x = (size_t)b * P + lp, y = (size_t)(b - 1) * P + lp;
-        float t = ws.top_sdf[x]; ws.top_sdf[x] = ws.top_sdf[y]; ws.top_sdf[y] = t;
-        t = ws.top_zafter[x]; ws.top_zafter[x] = ws.top_zafter[y]; ws.top_zafter[y] = t;
-        t = ws.top_zgen[x]; ws.top_zgen[x] = ws.top_zgen[y]; ws.top_zgen[y] = t;
-        const uint8_t l = ws.top_lvl[x]; ws.top_lvl[x] = ws.top_lvl[y]; ws.top_lvl[y] = l;
-        if (ws.top_slot) { const int32_t sl = ws.top_slot[x]; ws.top_slot[x] = ws.top_slot[y]; ws.top_slot[y] = sl; }
-        for (int k = 0; k < 3; ++k) {
-          const size_t px = ((size_t)b * 3 + k) * P + lp, py = ((size_t)(b - 1) * 3 + k) * P + lp;
-          t = ws.top_pt[px]; ws.top_pt[px] = ws.top_pt[py]; ws.top_pt[py] = t;
+  {   // the records are an unordered set until here: ascending |sdf| (stable), the minimum to slot 0 (renderer.py:316-319).
+      // The insertion sort runs on the keys in registers (the same comparisons in the same order as sorting the records
+      // themselves); every field is then read once and written once in its sorted place.
+    float key[DIST_MAX_BUFFER];
+    int ord[DIST_MAX_BUFFER];
+#pragma unroll
+    for (int b = 0; b < DIST_MAX_BUFFER; ++b) {
+      key[b] = (b < B) ? fabsf(ws.top_sdf[(size_t)b * P + lp]) : 0.f;
+      ord[b] = b;
+    }
+    bool moved = false;
+#pragma unroll
+    for (int a = 1; a < DIST_MAX_BUFFER; ++a) {
+      if (a < B) {
+        bool go = true;
+#pragma unroll
+        for (int b = a; b > 0; --b) {
+          go = go && (key[b] < key[b - 1]);
+          if (go) {
+            const float tk = key[b]; key[b] = key[b - 1]; key[b - 1] = tk;
+            const int to = ord[b]; ord[b] = ord[b - 1]; ord[b - 1] = to;
+            moved = true;
+          }
         }
       }
+    }
+    if (moved) {
+      // out[d] = in[ord[d]] without dynamic register indexing
+      auto permute_f = [&](float* base, size_t stride) {
+        float v[DIST_MAX_BUFFER];
+#pragma unroll
+        for (int b = 0; b < DIST_MAX_BUFFER; ++b) v[b] = (b < B) ? base[(size_t)b * stride + lp] : 0.f;
+#pragma unroll
+        for (int d = 0; d < DIST_MAX_BUFFER; ++d) {
+          if (d < B && ord[d] != d) {
+            float o = 0.f;
+#pragma unroll
+            for (int sidx = 0; sidx < DIST_MAX_BUFFER; ++sidx) o = (ord[d] == sidx) ? v[sidx] : o;
+            base[(size_t)d * stride + lp] = o;
+          }
+        }
+      };
+      permute_f(ws.top_sdf, (size_t)P);
+      permute_f(ws.top_zafter, (size_t)P);
+      permute_f(ws.top_zgen, (size_t)P);
+      for (int k = 0; k < 3; ++k) permute_f(ws.top_pt + (size_t)k * P, (size_t)3 * P);
+      {
+        int v[DIST_MAX_BUFFER];
+#pragma unroll
+        for (int b = 0; b < DIST_MAX_BUFFER; ++b) v[b] = (b < B) ? (int)ws.top_lvl[(size_t)b * P + lp] : 0;
+#pragma unroll
+        for (int d = 0; d < DIST_MAX_BUFFER; ++d) {
+          if (d < B && ord[d] != d) {
+            int o = 0;
+#pragma unroll
+            for (int sidx = 0; sidx < DIST_MAX_BUFFER; ++sidx) o = (ord[d] == sidx) ? v[sidx] : o;
+            ws.top_lvl[(size_t)d * P + lp] = (uint8_t)o;
+          }
+        }
+      }
+      if (ws.top_slot) {
+        int v[DIST_MAX_BUFFER];
+#pragma unroll
+        for (int b = 0; b < DIST_MAX_BUFFER; ++b) v[b] = (b < B) ? ws.top_slot[(size_t)b * P + lp] : -1;
+#pragma unroll
+        for (int d = 0; d < DIST_MAX_BUFFER; ++d) {
+          if (d < B && ord[d] != d) {
+            int o = -1;
+#pragma unroll
+            for (int sidx = 0; sidx < DIST_MAX_BUFFER; ++sidx) o = (ord[d] == sidx) ? v[sidx] : o;
+            ws.top_slot[(size_t)d * P + lp] = o;
+          }
+        }
+      }
+    }
   }
   const float s0 = ws.top_sdf[lp];
   const float entry = ws.entry[lp];
