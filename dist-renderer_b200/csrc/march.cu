@@ -66,6 +66,23 @@ __device__ __forceinline__ int warp_append(int32_t* counter, bool pred) {
   return pred ? base + __popc(m & ((1u << lane) - 1)) : -1;
 }
 
+// two appends at once: counters[0] / counters[1] are adjacent (8-byte aligned) and advance with ONE 64-bit atomic per warp
+__device__ __forceinline__ void warp_append2(int32_t* counters, bool p1, bool p2, int& idx1, int& idx2) {
+  const unsigned m1 = __ballot_sync(0xffffffffu, p1), m2 = __ballot_sync(0xffffffffu, p2);
+  idx1 = idx2 = -1;
+  if ((m1 | m2) == 0) return;
+  const int lane = threadIdx.x & 31;
+  const int leader = __ffs(m1 | m2) - 1;
+  unsigned long long base = 0;
+  if (lane == leader)
+    base = atomicAdd(reinterpret_cast<unsigned long long*>(counters),
+                     (unsigned long long)__popc(m1) | ((unsigned long long)__popc(m2) << 32));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  const unsigned below = (1u << lane) - 1;
+  if (p1) idx1 = (int)(uint32_t)base + __popc(m1 & below);
+  if (p2) idx2 = (int)(uint32_t)(base >> 32) + __popc(m2 & below);
+}
+
 // unit ray through pixel coordinates (x, y), world frame (renderer.py:39,190-200; :631-636 for pyramid levels)
 __device__ __forceinline__ void coord_ray(const Cam& cam, const float* R, float x, float y, float (&ray)[3]) {
   float hc[3], v[3];
@@ -408,13 +425,17 @@ __global__ void k_march_update(Cam cam, dist_march_t mp, dist_workspace_t ws, in
     view_atomic_max(ws.view_stat, VS_STEPS, v, step + 1);   // view v executed this step
     // compaction into the next step's two segments (without screening everything goes to segment 1)
     const bool to1 = live && (!scr || pred_far), to2 = live && !to1;
-    int idx = warp_append(ws.counts + 2 * (step + 1), to1);
-    const int idx2 = warp_append(ws.counts + 2 * (step + 1) + 1, to2);
-    if (idx2 >= 0) idx = SEG + idx2;
-    if (idx >= 0) {
-      float ray[3] = {ws.ray[lp], ws.ray[P + lp], ws.ray[2 * P + lp]}, p[3], c[3];
+    // the next query point does not depend on where the row lands: it is computed before the atomic, not behind it
+    float p[3] = {0.f, 0.f, 0.f};
+    if (live) {
+      float ray[3] = {ws.ray[lp], ws.ray[P + lp], ws.ray[2 * P + lp]}, c[3];
       load_view_pos(cam, v, c);
       point_on_ray(cam, c, ray, entry + znew, p);
+    }
+    int idx, idx2;
+    warp_append2(ws.counts + 2 * (step + 1), to1, to2, idx, idx2);
+    if (idx2 >= 0) idx = SEG + idx2;
+    if (idx >= 0) {
       nxt[idx] = lp;
       pts_nxt[(size_t)idx * 3] = p[0]; pts_nxt[(size_t)idx * 3 + 1] = p[1]; pts_nxt[(size_t)idx * 3 + 2] = p[2];
     }

@@ -150,7 +150,7 @@ typedef struct dist_workspace {
   int32_t* list_b;   /* [2*SEG] active ray list (pong) */
   float* pts;        /* [2][2*SEG][3] query points, ping-pong by step parity */
   float* sdf;        /* [2*SEG] decoder outputs of the current step */
-  int32_t* counts;   /* [2*(march_step + 2)] active rays per step and segment; zeroed by dist_render_depth_fwd */
+  int32_t* counts;   /* [2*(march_step + 2)] active rays per step and segment (8-byte aligned: a step's pair advances with one 64-bit atomic); zeroed by dist_render_depth_fwd */
   float* sdf_origin; /* [1] sdf at the origin (filler samples, renderer.py:539-540) */
   float* entry0;     /* [P] true unit-sphere entry depth; == entry except in DIST_MARCH_PYRAMID, where `entry` holds the
                         depth the full-resolution march starts from (inherited from the 1/2-resolution parent ray) */
